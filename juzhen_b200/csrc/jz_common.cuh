@@ -1,0 +1,59 @@
+// jz_common.cuh -- shared internals of libjz_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include <atomic>
+
+#include "../../include/jz_b200.h"
+
+namespace jz {
+
+struct Ctx {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 148;
+    int cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    std::atomic<uint64_t> launches{0};
+    int gemm_mode = JZ_GEMM_3XTF32;
+    int gemm_last_path = 0;
+};
+
+Ctx& ctx();
+int ensure_init();                                  // lazy jz_init(current device)
+int fail(int code, const char* fmt, ...);           // records jz_last_error(), returns code
+int cuda_fail(cudaError_t e, const char* what);     // JZ_ERR_CUDA with the CUDA error string
+
+inline cudaStream_t as_stream(jz_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// temporary workspace from the stream-ordered pool (bytes), released with ws_free
+int ws_alloc(void** p, size_t bytes, cudaStream_t s);
+int ws_free(void* p, cudaStream_t s);
+
+}  // namespace jz
+
+// launch + count + error check.  Every kernel of this library goes through here so
+// jz_launch_count() is an honest count of OUR launches.
+#define JZ_LAUNCH(kernel, grid, block, smem, stream, ...)                          \
+    do {                                                                           \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                \
+        ::jz::ctx().launches.fetch_add(1, std::memory_order_relaxed);              \
+        cudaError_t e__ = cudaPeekAtLastError();                                   \
+        if (e__ != cudaSuccess) return ::jz::cuda_fail(cudaGetLastError(), #kernel); \
+    } while (0)
+
+#define JZ_INIT_OR_RETURN()                      \
+    do {                                         \
+        int rc__ = ::jz::ensure_init();          \
+        if (rc__ != JZ_OK) return rc__;          \
+    } while (0)
+
+#define JZ_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return ::jz::cuda_fail(e__, #call); \
+    } while (0)

@@ -1,0 +1,443 @@
+// jz_elementwise.cu -- flat elementwise maps (SURVEY 8a rows a4,a5,a7,a8,a10 flat cases).
+//
+// All of these are HBM-bound streaming kernels: algorithmic traffic 4 B/elem (fill),
+// 8 B/elem (unary, affine, eleminv, copy, fused chain) or 12 B/elem (axpby, hadamard,
+// div).  Design for B200 (148 SMs, ~6.5 TB/s measured copy bandwidth):
+//   * 128-bit accesses (LDG.E.128 / STG.E.128), fully coalesced: a warp moves 512 B per
+//     instruction;
+//   * each thread keeps UNROLL (=4) independent 128-bit loads in flight before the
+//     first use (MLP 4 per thread, 64 B), 256 threads per CTA, so one CTA tile is 16 KB
+//     per operand;
+//   * grid = min(#tiles, 8 CTAs x 148 SMs) with a grid-stride loop over tiles, so the
+//     grid is an exact multiple of the SM count at full occupancy (2048 threads/SM);
+//   * scalar fall-back with the same tiling when a pointer is not 16-byte aligned
+//     (hstack column offsets, odd leading dimensions such as n = 1001);
+//   * the reference launched one 1024-thread block per 1024 elements with 4-byte
+//     accesses and cast the count to unsigned (cpp/cumatrix.cuh:59-62); here counts are
+//     size_t throughout (2^30-element matrices and beyond).
+#include "jz_common.cuh"
+#include "jz_math.cuh"
+
+namespace jz {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+// functors --------------------------------------------------------------------------
+template <int OP>
+struct UnaryF {
+    __device__ __forceinline__ float operator()(float x) const { return unary_op<OP>(x); }
+};
+struct AffineF {
+    float s1, a;
+    __device__ __forceinline__ float operator()(float x) const { return affine_rn(x, s1, a); }
+};
+struct ElemInvF {
+    float l;
+    __device__ __forceinline__ float operator()(float x) const { return eleminv_rn(x, l); }
+};
+struct CopyF {
+    __device__ __forceinline__ float operator()(float x) const { return x; }
+};
+struct AxpbyF {
+    float s1, s2;
+    __device__ __forceinline__ float operator()(float x, float y) const {
+        return __fadd_rn(__fmul_rn(s1, x), __fmul_rn(s2, y));  // cpp/core.hpp:427
+    }
+};
+struct MulF {
+    __device__ __forceinline__ float operator()(float x, float y) const { return __fmul_rn(x, y); }
+};
+struct DivF {  // a * (1/b): eleminv(1) then hadmd, two roundings (cpp/operators.hpp:270-274)
+    __device__ __forceinline__ float operator()(float x, float y) const {
+        return __fmul_rn(x, __fdiv_rn(1.0f, y));
+    }
+};
+
+// kernels ---------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(kThreads) map1_v4(float* out, const float* in, size_t n, F f) {
+    const size_t n4 = n >> 2;
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    const size_t tile = size_t(kThreads) * kUnroll;
+    for (size_t base = size_t(blockIdx.x) * tile; base < n4; base += size_t(gridDim.x) * tile) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            if (i < n4) v[u] = in4[i];
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            if (i < n4) {
+                float4 r;
+                r.x = f(v[u].x); r.y = f(v[u].y); r.z = f(v[u].z); r.w = f(v[u].w);
+                out4[i] = r;
+            }
+        }
+    }
+    // tail (n % 4 elements)
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = (n4 << 2) + threadIdx.x;
+        out[i] = f(in[i]);
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(kThreads) map1_s(float* out, const float* in, size_t n, F f) {
+    const size_t tile = size_t(kThreads) * kUnroll;
+    for (size_t base = size_t(blockIdx.x) * tile; base < n; base += size_t(gridDim.x) * tile) {
+        float v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            if (i < n) v[u] = in[i];
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            if (i < n) out[i] = f(v[u]);
+        }
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(kThreads) map2_v4(float* out, const float* a, const float* b, size_t n, F f) {
+    const size_t n4 = n >> 2;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    const size_t tile = size_t(kThreads) * kUnroll;
+    for (size_t base = size_t(blockIdx.x) * tile; base < n4; base += size_t(gridDim.x) * tile) {
+        float4 x[kUnroll], y[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            if (i < n4) { x[u] = a4[i]; y[u] = b4[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            if (i < n4) {
+                float4 r;
+                r.x = f(x[u].x, y[u].x); r.y = f(x[u].y, y[u].y);
+                r.z = f(x[u].z, y[u].z); r.w = f(x[u].w, y[u].w);
+                out4[i] = r;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = (n4 << 2) + threadIdx.x;
+        out[i] = f(a[i], b[i]);
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(kThreads) map2_s(float* out, const float* a, const float* b, size_t n, F f) {
+    const size_t tile = size_t(kThreads) * kUnroll;
+    for (size_t base = size_t(blockIdx.x) * tile; base < n; base += size_t(gridDim.x) * tile) {
+        float x[kUnroll], y[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            if (i < n) { x[u] = a[i]; y[u] = b[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            if (i < n) out[i] = f(x[u], y[u]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) fill_v4(float* out, size_t n, float val) {
+    const size_t n4 = n >> 2;
+    float4* out4 = reinterpret_cast<float4*>(out);
+    const float4 v = make_float4(val, val, val, val);
+    const size_t tile = size_t(kThreads) * kUnroll;
+    for (size_t base = size_t(blockIdx.x) * tile; base < n4; base += size_t(gridDim.x) * tile) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            if (i < n4) out4[i] = v;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[(n4 << 2) + threadIdx.x] = val;
+}
+
+__global__ void __launch_bounds__(kThreads) fill_s(float* out, size_t n, float val) {
+    for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += size_t(gridDim.x) * kThreads)
+        out[i] = val;
+}
+
+// fused chain: UNROLL x 4 values per thread in registers, every step applied to the
+// whole register tile so the per-step dispatch is amortised over 16 elements.
+__global__ void __launch_bounds__(kThreads) chain_v4(float* out, const float* in, size_t n, ChainParams c) {
+    const size_t n4 = n >> 2;
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    const size_t tile = size_t(kThreads) * kUnroll;
+    for (size_t base = size_t(blockIdx.x) * tile; base < n4; base += size_t(gridDim.x) * tile) {
+        float v[kUnroll * 4];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            float4 t = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (i < n4) t = in4[i];
+            v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
+        }
+        apply_chain<kUnroll * 4>(v, c);
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            if (i < n4) out4[i] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = (n4 << 2) + threadIdx.x;
+        float t[1] = {in[i]};
+        apply_chain<1>(t, c);
+        out[i] = t[0];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) chain_s(float* out, const float* in, size_t n, ChainParams c) {
+    for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += size_t(gridDim.x) * kThreads) {
+        float t[1] = {in[i]};
+        apply_chain<1>(t, c);
+        out[i] = t[0];
+    }
+}
+
+// fused Adam step (ml/util.cuh:152-163): same arithmetic, vectorised, 12 B read + 12 B write
+__global__ void __launch_bounds__(kThreads) adam_kernel(float* g, float* m, float* v, size_t n, float alpha,
+                                                        float beta1, float beta2, float eps, float bc1, float bc2) {
+    for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += size_t(gridDim.x) * kThreads) {
+        const float gi = g[i];
+        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        g[i] = alpha * (mi * bc1) / (sqrtf(vi * bc2) + eps);
+    }
+}
+
+static inline unsigned grid_for(size_t work_items_per_thread_group) {
+    // work_items = number of (kThreads*kUnroll)-sized tiles
+    const size_t cap = size_t(ctx().sm_count) * 8;
+    size_t g = work_items_per_thread_group < cap ? work_items_per_thread_group : cap;
+    return unsigned(g ? g : 1);
+}
+
+template <class F>
+static int launch_map1(float* out, const float* in, size_t n, F f, cudaStream_t s) {
+    if (n == 0) return JZ_OK;
+    if (!out || !in) return fail(JZ_ERR_ARG, "null pointer");
+    if (aligned16(out) && aligned16(in)) {
+        const size_t tiles = ceil_div(n >> 2, size_t(kThreads) * kUnroll);
+        JZ_LAUNCH((map1_v4<F>), grid_for(tiles), kThreads, 0, s, out, in, n, f);
+    } else {
+        const size_t tiles = ceil_div(n, size_t(kThreads) * kUnroll);
+        JZ_LAUNCH((map1_s<F>), grid_for(tiles), kThreads, 0, s, out, in, n, f);
+    }
+    return JZ_OK;
+}
+
+template <class F>
+static int launch_map2(float* out, const float* a, const float* b, size_t n, F f, cudaStream_t s) {
+    if (n == 0) return JZ_OK;
+    if (!out || !a || !b) return fail(JZ_ERR_ARG, "null pointer");
+    if (aligned16(out) && aligned16(a) && aligned16(b)) {
+        const size_t tiles = ceil_div(n >> 2, size_t(kThreads) * kUnroll);
+        JZ_LAUNCH((map2_v4<F>), grid_for(tiles), kThreads, 0, s, out, a, b, n, f);
+    } else {
+        const size_t tiles = ceil_div(n, size_t(kThreads) * kUnroll);
+        JZ_LAUNCH((map2_s<F>), grid_for(tiles), kThreads, 0, s, out, a, b, n, f);
+    }
+    return JZ_OK;
+}
+
+// ---- exhaustive accuracy sweep (test support): compares unary_op<OP> with an fp64
+// evaluation rounded once to fp32 over a range of fp32 bit patterns.
+template <int OP>
+__device__ double ref64(double x) {
+    if constexpr (OP == JZ_EXP) return exp(x);
+    else if constexpr (OP == JZ_LOG) return log(x);
+    else if constexpr (OP == JZ_TANH) return tanh(x);
+    else if constexpr (OP == JZ_DTANH) {  // exact sech^2, cancellation-free
+        const double e = exp(-2.0 * fabs(x));
+        const double s = 1.0 + e;
+        return 4.0 * e / (s * s);
+    } else if constexpr (OP == JZ_SQUARE) return x * x;
+    else if constexpr (OP == JZ_SQRT) return sqrt(x);
+    else if constexpr (OP == JZ_RELU) return x > 0.0 ? x : 0.0;
+    else return x > 0.0 ? 1.0 : 0.0;
+}
+
+__device__ __forceinline__ int64_t ordered(float f) {
+    const uint32_t u = __float_as_uint(f);
+    const int64_t mag = int64_t(u & 0x7fffffffu);
+    return (u >> 31) ? -mag : mag;
+}
+
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+template <int OP>
+__global__ void ulp_sweep_kernel(uint32_t lo, uint32_t hi, unsigned long long* packed_max) {
+    unsigned long long best = 0;
+    for (uint64_t b = uint64_t(lo) + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; b < hi;
+         b += uint64_t(gridDim.x) * blockDim.x) {
+        const float x = __uint_as_float(uint32_t(b));
+        if (isnan(x) || isinf(x)) continue;
+        const float got = unary_op<OP>(x);
+        const float want = float(ref64<OP>(double(x)));
+        if (isnan(want) || isnan(got)) {
+            if (isnan(want) != isnan(got)) best = umax64(best, (0xFFFFFFFFull << 32) | b);
+            continue;
+        }
+        if (isinf(want) || isinf(got)) {
+            if (want != got) {
+                // overflow boundary: count distance to FLT_MAX side as 1 ulp steps
+                const float w2 = isinf(want) ? copysignf(3.402823466e38f, want) : want;
+                const float g2 = isinf(got) ? copysignf(3.402823466e38f, got) : got;
+                int64_t d = ordered(w2) - ordered(g2);
+                d = (d < 0 ? -d : d) + 1;
+                best = umax64(best, (uint64_t(d) << 32) | b);
+            }
+            continue;
+        }
+        int64_t d = ordered(want) - ordered(got);
+        if (d < 0) d = -d;
+        if (d > 0xFFFFFFFEll) d = 0xFFFFFFFEll;
+        const unsigned long long p = (uint64_t(d) << 32) | b;
+        best = umax64(best, p);
+    }
+    // warp then global max
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = umax64(best, other);
+    }
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(packed_max, best);
+}
+
+}  // namespace jz
+
+using namespace jz;
+
+extern "C" {
+
+int jz_fill(float* x, size_t n, float value, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    if (n == 0) return JZ_OK;
+    if (!x) return fail(JZ_ERR_ARG, "jz_fill: null pointer");
+    cudaStream_t s = as_stream(stream);
+    if (aligned16(x)) {
+        JZ_LAUNCH(fill_v4, grid_for(ceil_div(n >> 2, size_t(kThreads) * kUnroll)), kThreads, 0, s, x, n, value);
+    } else {
+        JZ_LAUNCH(fill_s, grid_for(ceil_div(n, size_t(kThreads) * kUnroll)), kThreads, 0, s, x, n, value);
+    }
+    return JZ_OK;
+}
+
+int jz_copy(float* dst, const float* src, size_t n, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    return launch_map1(dst, src, n, CopyF{}, as_stream(stream));
+}
+
+int jz_affine(float* out, const float* in, size_t n, float s1, float a, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    return launch_map1(out, in, n, AffineF{s1, a}, as_stream(stream));
+}
+
+int jz_eleminv(float* out, const float* in, size_t n, float l, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    return launch_map1(out, in, n, ElemInvF{l}, as_stream(stream));
+}
+
+int jz_unary(int op, float* out, const float* in, size_t n, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    cudaStream_t s = as_stream(stream);
+    switch (op) {
+        case JZ_EXP: return launch_map1(out, in, n, UnaryF<JZ_EXP>{}, s);
+        case JZ_LOG: return launch_map1(out, in, n, UnaryF<JZ_LOG>{}, s);
+        case JZ_TANH: return launch_map1(out, in, n, UnaryF<JZ_TANH>{}, s);
+        case JZ_DTANH: return launch_map1(out, in, n, UnaryF<JZ_DTANH>{}, s);
+        case JZ_SQUARE: return launch_map1(out, in, n, UnaryF<JZ_SQUARE>{}, s);
+        case JZ_SQRT: return launch_map1(out, in, n, UnaryF<JZ_SQRT>{}, s);
+        case JZ_RELU: return launch_map1(out, in, n, UnaryF<JZ_RELU>{}, s);
+        case JZ_DRELU: return launch_map1(out, in, n, UnaryF<JZ_DRELU>{}, s);
+        default: return fail(JZ_ERR_ARG, "jz_unary: unknown op %d", op);
+    }
+}
+
+int jz_axpby(float* out, const float* a, const float* b, size_t n, float s1, float s2, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    return launch_map2(out, a, b, n, AxpbyF{s1, s2}, as_stream(stream));
+}
+
+int jz_hadamard(float* out, const float* a, const float* b, size_t n, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    return launch_map2(out, a, b, n, MulF{}, as_stream(stream));
+}
+
+int jz_div(float* out, const float* a, const float* b, size_t n, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    return launch_map2(out, a, b, n, DivF{}, as_stream(stream));
+}
+
+int jz_chain(float* out, const float* in, size_t n, const jz_step* steps, int nsteps, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    ChainParams c;
+    if (make_chain(c, steps, nsteps) != JZ_OK) return fail(JZ_ERR_ARG, "jz_chain: bad step list");
+    if (n == 0) return JZ_OK;
+    if (!out || !in) return fail(JZ_ERR_ARG, "jz_chain: null pointer");
+    cudaStream_t s = as_stream(stream);
+    if (aligned16(out) && aligned16(in)) {
+        JZ_LAUNCH(chain_v4, grid_for(ceil_div(n >> 2, size_t(kThreads) * kUnroll)), kThreads, 0, s, out, in, n, c);
+    } else {
+        JZ_LAUNCH(chain_s, grid_for(ceil_div(n, size_t(kThreads) * kUnroll)), kThreads, 0, s, out, in, n, c);
+    }
+    return JZ_OK;
+}
+
+int jz_adam_update(float* g, float* m, float* v, size_t n, float alpha, float beta1, float beta2, float eps,
+                   float bc1, float bc2, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    if (n == 0) return JZ_OK;
+    if (!g || !m || !v) return fail(JZ_ERR_ARG, "jz_adam_update: null pointer");
+    JZ_LAUNCH(adam_kernel, grid_for(ceil_div(n, size_t(kThreads) * kUnroll)), kThreads, 0, as_stream(stream), g, m,
+              v, n, alpha, beta1, beta2, eps, bc1, bc2);
+    return JZ_OK;
+}
+
+int jz_unary_ulp_sweep(int op, uint32_t lo_bits, uint32_t hi_bits, uint32_t* max_ulp_host,
+                       uint32_t* worst_bits_host, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    cudaStream_t s = as_stream(stream);
+    void* d = nullptr;
+    int rc = ws_alloc(&d, sizeof(unsigned long long), s);
+    if (rc != JZ_OK) return rc;
+    JZ_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s));
+    auto* pm = static_cast<unsigned long long*>(d);
+    const unsigned grid = unsigned(ctx().sm_count) * 8;
+    switch (op) {
+        case JZ_EXP: JZ_LAUNCH(ulp_sweep_kernel<JZ_EXP>, grid, 256, 0, s, lo_bits, hi_bits, pm); break;
+        case JZ_LOG: JZ_LAUNCH(ulp_sweep_kernel<JZ_LOG>, grid, 256, 0, s, lo_bits, hi_bits, pm); break;
+        case JZ_TANH: JZ_LAUNCH(ulp_sweep_kernel<JZ_TANH>, grid, 256, 0, s, lo_bits, hi_bits, pm); break;
+        case JZ_DTANH: JZ_LAUNCH(ulp_sweep_kernel<JZ_DTANH>, grid, 256, 0, s, lo_bits, hi_bits, pm); break;
+        case JZ_SQUARE: JZ_LAUNCH(ulp_sweep_kernel<JZ_SQUARE>, grid, 256, 0, s, lo_bits, hi_bits, pm); break;
+        case JZ_SQRT: JZ_LAUNCH(ulp_sweep_kernel<JZ_SQRT>, grid, 256, 0, s, lo_bits, hi_bits, pm); break;
+        default: ws_free(d, s); return fail(JZ_ERR_ARG, "jz_unary_ulp_sweep: op %d not swept", op);
+    }
+    unsigned long long h = 0;
+    JZ_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
+    JZ_CUDA(cudaStreamSynchronize(s));
+    ws_free(d, s);
+    if (max_ulp_host) *max_ulp_host = uint32_t(h >> 32);
+    if (worst_bits_host) *worst_bits_host = uint32_t(h & 0xffffffffu);
+    return JZ_OK;
+}
+
+}  // extern "C"

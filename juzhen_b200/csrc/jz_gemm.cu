@@ -1,0 +1,730 @@
+// jz_gemm.cu -- the GEMM behind Matrix<CUDAfloat>::dot / operator* (SURVEY 8a row a17):
+//     C(m x n, ldc) = alpha * op(A)(m x k) * op(B)(k x n) + beta * C        (column-major)
+// replacing cublasSgemm (cpp/cumatrix.cu:177-197).  No cuBLAS anywhere.
+//
+// Main path (sm_100a): TMA -> shared memory (128B swizzle) -> tcgen05.mma.kind::tf32 with the
+// fp32 accumulator in TMEM -> tcgen05.ld -> coalesced column-major stores.
+//   * warp-specialised CTA: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+//     warps 2..5 = epilogue (one TMEM lane quarter each);
+//   * CG = 2: a CTA pair (cluster 2x1x1, cta_group::2) computes one 256 x 256 tile; each CTA
+//     loads its 128 rows of A and its 128-column half of B, the leader issues M=256 N=256 K=8
+//     MMAs that read both CTAs' shared memory.  CG = 1 is the single-SM 128 x 256 variant;
+//   * 3xTF32 (default, fp32 accuracy): operands are pre-split into tf32 "hi" and "lo" parts
+//     (hi = rna_tf32(x), lo = rna_tf32(x - hi)) and every k-block issues
+//     A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same TMEM accumulator;
+//   * both operands are consumed K-major (the canonical UMMA layout): column-major B and
+//     flagged-transpose A already are; the other two cases are re-laid out by the same
+//     pre-pass that does the hi/lo split (a tiled transpose through shared memory).
+//     Pre-pass traffic is O(mk + kn) against O(mnk) math: 6% at 4096^3, 1.5% at 16384^3.
+//
+// Fallback path: a bounds-checked fp32 FMA (SIMT) kernel for shapes TMA cannot address
+// (n = 1001 in tests/testEigen.cu, ld = 10 in the MNIST head), for tiny problems and for
+// mode JZ_GEMM_FP32_SIMT; rank-1 products (k == 1: the reference's broadcast idiom) are a
+// streaming outer-product kernel.
+#include <cuda.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "jz_common.cuh"
+#include "jz_math.cuh"
+
+namespace jz {
+
+// ======================================================================= SIMT fallback
+constexpr int SBM = 64, SBN = 64, SBK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_simt_kernel(size_t m, size_t n, size_t k, float alpha, const float* A,
+                                                         size_t lda, const float* B, size_t ldb, float beta, float* C,
+                                                         size_t ldc, ChainParams chain) {
+    __shared__ float As[SBK][SBM + 4];
+    __shared__ float Bs[SBK][SBN + 4];
+    const int t = threadIdx.x;
+    const size_t i0 = size_t(blockIdx.x) * SBM, j0 = size_t(blockIdx.y) * SBN;
+    const int tx = t & 15, ty = t >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = 0.0f;
+
+    for (size_t k0 = 0; k0 < k; k0 += SBK) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            // A tile: op(A)(i, kk)
+            int ii, kk;
+            if (!TA) { ii = t & 63; kk = (t >> 6) + 4 * r; }
+            else { kk = t & 15; ii = (t >> 4) + 16 * r; }
+            const size_t gi = i0 + ii, gk = k0 + kk;
+            float v = 0.0f;
+            if (gi < m && gk < k) v = TA ? A[gi * lda + gk] : A[gk * lda + gi];
+            As[kk][ii] = v;
+            // B tile: op(B)(kk, j)
+            int jj, kb;
+            if (!TB) { kb = t & 15; jj = (t >> 4) + 16 * r; }
+            else { jj = t & 63; kb = (t >> 6) + 4 * r; }
+            const size_t gj = j0 + jj, gk2 = k0 + kb;
+            float w = 0.0f;
+            if (gj < n && gk2 < k) w = TB ? B[gk2 * ldb + gj] : B[gj * ldb + gk2];
+            Bs[kb][jj] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < SBK; kk++) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][tx * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][ty * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const size_t gj = j0 + ty * 4 + c;
+        if (gj >= n) continue;
+        float v[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const size_t gi = i0 + tx * 4 + r;
+            float x = alpha * acc[r][c];
+            if (beta != 0.0f && gi < m) x += beta * C[gj * ldc + gi];
+            v[r] = x;
+        }
+        if (chain.n) apply_chain<4>(v, chain);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const size_t gi = i0 + tx * 4 + r;
+            if (gi < m) C[gj * ldc + gi] = v[r];
+        }
+    }
+}
+
+static int launch_simt(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                       const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain,
+                       cudaStream_t s) {
+    const size_t gx = ceil_div(m, SBM), gy = ceil_div(n, SBN);
+    if (gy > 65535) return fail(JZ_ERR_UNSUPPORTED, "simt gemm: n too large for the fallback kernel");
+    const dim3 grid((unsigned)gx, (unsigned)gy, 1);
+    if (!ta && !tb) JZ_LAUNCH((sgemm_simt_kernel<false, false>), grid, 256, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    else if (ta && !tb) JZ_LAUNCH((sgemm_simt_kernel<true, false>), grid, 256, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    else if (!ta && tb) JZ_LAUNCH((sgemm_simt_kernel<false, true>), grid, 256, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    else JZ_LAUNCH((sgemm_simt_kernel<true, true>), grid, 256, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    ctx().gemm_last_path = 2;
+    return JZ_OK;
+}
+
+// rank-1: C = alpha*u*v^T (+beta*C) ; u = op(A)(:,0) (stride su), v = op(B)(0,:) (stride sv).
+// u == nullptr means the product term is absent (k == 0).
+__global__ void __launch_bounds__(256) rank1_kernel(size_t m, size_t n, float alpha, const float* u, size_t su,
+                                                    const float* v, size_t sv, float beta, float* C, size_t ldc,
+                                                    ChainParams chain) {
+    for (size_t j = blockIdx.y; j < n; j += gridDim.y) {
+        const float vj = u ? alpha * v[j * sv] : 0.0f;
+        for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < m; i += size_t(gridDim.x) * 256) {
+            float x[1] = {u ? u[i * su] * vj : 0.0f};
+            if (beta != 0.0f) x[0] += beta * C[j * ldc + i];
+            if (chain.n) apply_chain<1>(x, chain);
+            C[j * ldc + i] = x[0];
+        }
+    }
+}
+
+// ======================================================================= tcgen05 path
+namespace tc {
+
+constexpr int BK = 32;               // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;            // tf32: 32 bytes per MMA k-step
+constexpr int TILE_M = 128;          // rows of A per CTA (TMEM lanes)
+constexpr int TILE_N = 256;          // accumulator columns
+constexpr int A_BYTES = TILE_M * BK * 4;  // 16 KB
+constexpr int NUM_THREADS = 192;
+
+template <int CG> __host__ __device__ constexpr int b_rows() { return CG == 2 ? 128 : 256; }
+template <int CG> __host__ __device__ constexpr int b_bytes() { return b_rows<CG>() * BK * 4; }
+template <int CG, bool SPLIT> __host__ __device__ constexpr int stage_bytes() { return (SPLIT ? 2 : 1) * (A_BYTES + b_bytes<CG>()); }
+template <int CG, bool SPLIT> __host__ __device__ constexpr int num_stages() {
+    constexpr int s = (227 * 1024 - 2048) / stage_bytes<CG, SPLIT>();
+    return s > 6 ? 6 : s;
+}
+template <int CG, bool SPLIT> __host__ __device__ constexpr int smem_bytes() {
+    return num_stages<CG, SPLIT>() * stage_bytes<CG, SPLIT>() + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    if constexpr (CG == 2) {
+        // both CTAs of the pair signal the LEADER's barrier (peer bit cleared)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+            : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    if constexpr (CG == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+            "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+            "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// tcgen05.commit: arrive on `bar` (in every CTA of the pair for CG == 2) when all prior MMAs retire
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if constexpr (CG == 2) {
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+            "h"((uint16_t)3)
+            : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    if constexpr (CG == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units
+    d |= uint64_t(0) << 16;                   // leading byte offset: unused for swizzled K-major
+    d |= uint64_t(1024 >> 4) << 32;           // stride byte offset between 8-row groups
+    d |= uint64_t(1) << 46;                   // descriptor version (sm_100)
+    d |= uint64_t(2) << 61;                   // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: tf32 x tf32 -> f32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+struct GemmArgs {
+    size_t m, n, k;
+    float alpha, beta;
+    float* C;
+    size_t ldc;
+    unsigned tiles_m, tiles_n;  // in units of (CG*128) x 256 tiles
+    ChainParams chain;
+};
+
+// One (CG*128) x 256 output tile per CTA group.  tmA*/tmB*: [rows][K] K-major tensor maps.
+template <int CG, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const GemmArgs args) {
+    constexpr int STAGES = num_stages<CG, SPLIT>();
+    constexpr int STAGE_BYTES = stage_bytes<CG, SPLIT>();
+    constexpr int B_BYTES = b_bytes<CG>();
+    constexpr uint32_t IDESC = make_idesc_tf32(CG * 128, TILE_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    // barriers: full[STAGES], empty[STAGES], tmem_full, then the TMEM base slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+    uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+
+    // tile coordinates (grouped rasterisation for L2 reuse of the A / B panels)
+    const unsigned tile = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;
+    constexpr unsigned GROUP = 8;
+    const unsigned per_group = GROUP * args.tiles_n;
+    const unsigned group_id = tile / per_group;
+    const unsigned first_m = group_id * GROUP;
+    const unsigned group_m = args.tiles_m - first_m < GROUP ? args.tiles_m - first_m : GROUP;
+    const unsigned tm = first_m + (tile % per_group) % group_m;
+    const unsigned tn = (tile % per_group) / group_m;
+    const int m0 = int(tm) * (CG * TILE_M) + int(rank) * TILE_M;  // first row of this CTA
+    const int n0 = int(tn) * TILE_N;
+    const int nb0 = n0 + (CG == 2 ? int(rank) * 128 : 0);         // first B row (= C column) this CTA loads
+    const int num_kb = int((args.k + BK - 1) / BK);
+
+    if (warp == 0 && elect_one()) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+        if (SPLIT) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+        }
+    }
+    if (warp == 1) {
+        if (elect_one()) {
+            for (int s = 0; s < STAGES; s++) {
+                mbar_init(full_bar(s), 1);
+                mbar_init(empty_bar(s), 1);
+            }
+            mbar_init(tmem_full_bar, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<CG>(tmem_slot, TILE_N);
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < num_kb; kb++) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                if (leader) mbar_arrive_expect_tx(full_bar(stage), uint32_t(STAGE_BYTES) * CG);
+                const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                const int kc = kb * BK;
+                tma_load_2d<CG>(sa, &tmA_hi, full_bar(stage), kc, m0);
+                tma_load_2d<CG>(sa + A_BYTES, &tmB_hi, full_bar(stage), kc, nb0);
+                if (SPLIT) {
+                    tma_load_2d<CG>(sa + A_BYTES + B_BYTES, &tmA_lo, full_bar(stage), kc, m0);
+                    tma_load_2d<CG>(sa + 2 * A_BYTES + B_BYTES, &tmB_lo, full_bar(stage), kc, nb0);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < num_kb; kb++) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint32_t a_hi = sa, b_hi = sa + A_BYTES;
+                    const uint32_t a_lo = sa + A_BYTES + B_BYTES, b_lo = sa + 2 * A_BYTES + B_BYTES;
+                    uint32_t first = kb == 0 ? 0u : 1u;
+                    if (SPLIT) {
+#pragma unroll
+                        for (int ks = 0; ks < BK / UMMA_K; ks++) {
+                            umma_tf32<CG>(tmem_base, make_smem_desc(a_lo + ks * 32), make_smem_desc(b_hi + ks * 32), IDESC, first);
+                            first = 1u;
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < BK / UMMA_K; ks++)
+                            umma_tf32<CG>(tmem_base, make_smem_desc(a_hi + ks * 32), make_smem_desc(b_lo + ks * 32), IDESC, 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ks++) {
+                        umma_tf32<CG>(tmem_base, make_smem_desc(a_hi + ks * 32), make_smem_desc(b_hi + ks * 32), IDESC, first);
+                        first = 1u;
+                    }
+                    umma_commit<CG>(empty_bar(stage));                       // frees this smem stage (both CTAs)
+                    if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar);    // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global (column-major) =====================
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int lane = threadIdx.x & 31;
+        const size_t row = size_t(m0) + quarter * 32 + lane;
+        const bool row_ok = row < args.m;
+        float* crow = args.C + row;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+            if (size_t(n0 + c0) >= args.n) break;  // warp-uniform
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), r);
+            float v[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) v[c] = args.alpha * __uint_as_float(r[c]);
+            if (args.beta != 0.0f) {
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const size_t col = size_t(n0 + c0 + c);
+                    if (row_ok && col < args.n) v[c] += args.beta * crow[col * args.ldc];
+                }
+            }
+            if (args.chain.n) apply_chain<32>(v, args.chain);
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const size_t col = size_t(n0 + c0 + c);
+                if (row_ok && col < args.n) crow[col * args.ldc] = v[c];  // a warp writes 32 consecutive floats
+            }
+        }
+    }
+
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc<CG>(tmem_base, TILE_N);
+}
+
+// ----------------------------------------------------------------------- operand pre-pass
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(__fsub_rn(x, hi));  // x - hi is exact in fp32
+    if (!isfinite(hi)) { hi = x; lo = 0.0f; }  // keep inf/nan semantics, avoid inf - inf
+}
+
+// source already K-major: src(r, kk) at r*ld + kk ; dst[r*kp + kk]
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) prep_kmajor_kernel(float* hi, float* lo, size_t kp, const float* src, size_t ld,
+                                                          size_t rows, size_t k) {
+    for (size_t r = size_t(blockIdx.y) * blockDim.y + threadIdx.y; r < rows; r += size_t(gridDim.y) * blockDim.y) {
+        for (size_t kk = size_t(blockIdx.x) * blockDim.x + threadIdx.x; kk < k; kk += size_t(gridDim.x) * blockDim.x) {
+            const float x = src[r * ld + kk];
+            if (SPLIT) {
+                float h, l;
+                split_tf32(x, h, l);
+                hi[r * kp + kk] = h;
+                lo[r * kp + kk] = l;
+            } else {
+                hi[r * kp + kk] = x;
+            }
+        }
+    }
+}
+
+// source MN-major: src(r, kk) at kk*ld + r ; dst[r*kp + kk]   (tiled transpose)
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) prep_transpose_kernel(float* hi, float* lo, size_t kp, const float* src,
+                                                             size_t ld, size_t rows, size_t k, size_t tiles_r,
+                                                             size_t tiles_k) {
+    __shared__ float tile[32][33];
+    const size_t ntiles = tiles_r * tiles_k;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t tr = t % tiles_r, tk = t / tiles_r;
+        const size_t r0 = tr * 32, k0 = tk * 32;
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+            const size_t kk = k0 + threadIdx.y + q, r = r0 + threadIdx.x;
+            if (kk < k && r < rows) tile[threadIdx.y + q][threadIdx.x] = src[kk * ld + r];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+            const size_t r = r0 + threadIdx.y + q, kk = k0 + threadIdx.x;
+            if (r < rows && kk < k) {
+                const float x = tile[threadIdx.x][threadIdx.y + q];
+                if (SPLIT) {
+                    float h, l;
+                    split_tf32(x, h, l);
+                    hi[r * kp + kk] = h;
+                    lo[r * kp + kk] = l;
+                } else {
+                    hi[r * kp + kk] = x;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+// [rows][k] fp32, row stride `stride_elems`, box = 32 x box_rows, 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const float* base, size_t rows, size_t k, size_t stride_elems, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(JZ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {cuuint64_t(k), cuuint64_t(rows)};
+    cuuint64_t strides[1] = {cuuint64_t(stride_elems) * sizeof(float)};
+    cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(JZ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+    return JZ_OK;
+}
+
+static int g_cg = 0;  // 0 = auto (2), else forced via JZ_GEMM_CG
+static int pick_cg() {
+    if (g_cg) return g_cg;
+    const char* e = std::getenv("JZ_GEMM_CG");
+    g_cg = (e && e[0] == '1') ? 1 : 2;
+    return g_cg;
+}
+
+struct Operand {
+    const float* hi = nullptr;
+    const float* lo = nullptr;
+    size_t stride = 0;     // elements between consecutive rows of the K-major image
+    void* owned = nullptr; // workspace to release
+};
+
+// Build the K-major image(s) of an operand.  kmajor_src: src(r,kk) at r*ld+kk, else at kk*ld+r.
+static int prepare_operand(Operand& op, const float* src, size_t ld, bool kmajor_src, size_t rows, size_t k,
+                           bool split, cudaStream_t s) {
+    if (!split && kmajor_src && ld % 4 == 0 && aligned16(src)) {  // TF32 mode: TMA straight from the source
+        op.hi = src;
+        op.stride = ld;
+        return JZ_OK;
+    }
+    const size_t kp = (k + 3) & ~size_t(3);
+    const size_t elems = rows * kp;
+    int rc = ws_alloc(&op.owned, (split ? 2 : 1) * elems * sizeof(float), s);
+    if (rc != JZ_OK) return rc;
+    float* hi = static_cast<float*>(op.owned);
+    float* lo = split ? hi + elems : nullptr;
+    op.hi = hi;
+    op.lo = lo;
+    op.stride = kp;
+    const size_t cap = size_t(ctx().sm_count) * 8;
+    if (kmajor_src) {
+        unsigned tx = 1;
+        while (tx < 256 && tx < k) tx <<= 1;
+        const unsigned ty = 256 / tx;
+        size_t gx = ceil_div(k, tx), gy = ceil_div(rows, ty);
+        if (gx > 1024) gx = 1024;
+        if (gy > 32768) gy = 32768;
+        const dim3 grid((unsigned)gx, (unsigned)gy, 1), block(tx, ty, 1);
+        if (split) JZ_LAUNCH((prep_kmajor_kernel<true>), grid, block, 0, s, hi, lo, kp, src, ld, rows, k);
+        else JZ_LAUNCH((prep_kmajor_kernel<false>), grid, block, 0, s, hi, lo, kp, src, ld, rows, k);
+    } else {
+        const size_t tiles_r = ceil_div(rows, 32), tiles_k = ceil_div(k, 32);
+        const size_t nt = tiles_r * tiles_k;
+        const unsigned grid = unsigned(nt < cap * 4 ? nt : cap * 4);
+        const dim3 block(32, 8, 1);
+        if (split) JZ_LAUNCH((prep_transpose_kernel<true>), grid, block, 0, s, hi, lo, kp, src, ld, rows, k, tiles_r, tiles_k);
+        else JZ_LAUNCH((prep_transpose_kernel<false>), grid, block, 0, s, hi, lo, kp, src, ld, rows, k, tiles_r, tiles_k);
+    }
+    return JZ_OK;
+}
+
+template <int CG, bool SPLIT>
+static int launch_tc(const Operand& a, const Operand& b, const GemmArgs& args_in, cudaStream_t s) {
+    GemmArgs args = args_in;
+    args.tiles_m = unsigned(ceil_div(args.m, size_t(CG * TILE_M)));
+    args.tiles_n = unsigned(ceil_div(args.n, size_t(TILE_N)));
+    alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = make_map(&ma_hi, a.hi, args.m, args.k, a.stride, TILE_M)) != JZ_OK) return rc;
+    if ((rc = make_map(&mb_hi, b.hi, args.n, args.k, b.stride, b_rows<CG>())) != JZ_OK) return rc;
+    if (SPLIT) {
+        if ((rc = make_map(&ma_lo, a.lo, args.m, args.k, a.stride, TILE_M)) != JZ_OK) return rc;
+        if ((rc = make_map(&mb_lo, b.lo, args.n, args.k, b.stride, b_rows<CG>())) != JZ_OK) return rc;
+    } else {
+        ma_lo = ma_hi;
+        mb_lo = mb_hi;
+    }
+    auto kern = gemm_tcgen05_kernel<CG, SPLIT>;
+    constexpr int SMEM = smem_bytes<CG, SPLIT>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        JZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(args.tiles_m * args.tiles_n * CG, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, args);
+    ctx().launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return cuda_fail(e, "gemm_tcgen05_kernel launch");
+    return JZ_OK;
+}
+
+static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                   const float* B, size_t ldb, float beta, float* C, size_t ldc, bool split, const ChainParams& chain,
+                   cudaStream_t s) {
+    Operand a, b;
+    int rc = prepare_operand(a, A, lda, /*kmajor_src=*/ta != 0, m, k, split, s);
+    if (rc == JZ_OK) rc = prepare_operand(b, B, ldb, /*kmajor_src=*/tb == 0, n, k, split, s);
+    if (rc == JZ_OK) {
+        GemmArgs args;
+        args.m = m; args.n = n; args.k = k;
+        args.alpha = alpha; args.beta = beta;
+        args.C = C; args.ldc = ldc;
+        args.tiles_m = args.tiles_n = 0;
+        args.chain = chain;
+        const int cg = pick_cg();
+        if (cg == 2) rc = split ? launch_tc<2, true>(a, b, args, s) : launch_tc<2, false>(a, b, args, s);
+        else rc = split ? launch_tc<1, true>(a, b, args, s) : launch_tc<1, false>(a, b, args, s);
+    }
+    if (a.owned) ws_free(a.owned, s);
+    if (b.owned) ws_free(b.owned, s);
+    if (rc == JZ_OK) ctx().gemm_last_path = 1;
+    return rc;
+}
+
+}  // namespace tc
+
+static int gemm_entry(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                      const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain, int mode,
+                      cudaStream_t s) {
+    if (m == 0 || n == 0) return JZ_OK;
+    if (!C) return fail(JZ_ERR_ARG, "jz_gemm: null C");
+    if (ldc < m) return fail(JZ_ERR_SHAPE, "jz_gemm: ldc < m");
+    if (mode < 0) mode = ctx().gemm_mode;
+    if (mode > JZ_GEMM_BF16) return fail(JZ_ERR_ARG, "jz_gemm: bad mode %d", mode);
+    if (k > 0) {
+        if (!A || !B) return fail(JZ_ERR_ARG, "jz_gemm: null operand");
+        if (lda < (ta ? k : m) || ldb < (tb ? n : k)) return fail(JZ_ERR_SHAPE, "jz_gemm: leading dimension too small");
+    }
+    const size_t cap = size_t(ctx().sm_count) * 8;
+    if (k <= 1) {  // k == 0: C = chain(beta*C); k == 1: rank-1 update (the reference's broadcast idiom)
+        const float* u = k ? A : nullptr;
+        const float* v = k ? B : nullptr;
+        const size_t su = ta ? lda : 1, sv = tb ? 1 : ldb;
+        size_t gx = ceil_div(m, size_t(256));
+        if (gx > cap) gx = cap;
+        size_t gy = ceil_div(cap * 4, gx);
+        if (gy > n) gy = n;
+        if (gy > 65535) gy = 65535;
+        const dim3 grid((unsigned)gx, (unsigned)gy, 1);
+        JZ_LAUNCH(rank1_kernel, grid, 256, 0, s, m, n, alpha, u, su, v, sv, beta, C, ldc, chain);
+        ctx().gemm_last_path = 3;
+        return JZ_OK;
+    }
+    const bool want_tc = (mode == JZ_GEMM_3XTF32 || mode == JZ_GEMM_TF32 || mode == JZ_GEMM_BF16) && ctx().cc_major == 10;
+    const bool big_enough = m >= 64 && n >= 64 && k >= 32 && (double(m) * double(n) * double(k) >= double(1 << 22));
+    const bool fits_i32 = m < (size_t(1) << 31) && n < (size_t(1) << 31) && k < (size_t(1) << 31);
+    static const bool force_simt = std::getenv("JZ_GEMM_FORCE_SIMT") != nullptr;
+    if (want_tc && big_enough && fits_i32 && !force_simt) {
+        // BF16 mode currently rides the TF32 kernel (a strict accuracy superset of bf16 inputs)
+        const bool split = mode == JZ_GEMM_3XTF32;
+        return tc::gemm_tc(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, split, chain, s);
+    }
+    return launch_simt(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+}
+
+}  // namespace jz
+
+using namespace jz;
+
+extern "C" {
+
+int jz_gemm(int transA, int transB, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+            const float* B, size_t ldb, float beta, float* C, size_t ldc, int mode, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    ChainParams chain;
+    chain.n = 0;
+    return gemm_entry(transA, transB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, mode, as_stream(stream));
+}
+
+int jz_gemm_chain(int transA, int transB, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                  const float* B, size_t ldb, float* C, size_t ldc, const jz_step* steps, int nsteps, int mode,
+                  jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    ChainParams chain;
+    if (make_chain(chain, steps, nsteps) != JZ_OK) return fail(JZ_ERR_ARG, "jz_gemm_chain: bad step list");
+    return gemm_entry(transA, transB, m, n, k, alpha, A, lda, B, ldb, 0.0f, C, ldc, chain, mode, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// jz_math.cuh -- per-element device math shared by the map kernels, the fused chain,
+// the GEMM epilogue and the accuracy sweep.
+//
+// Parity target (BASELINE.json north_star): <= 2 ulp against the reference's g++ CPU build,
+// which evaluates exp/log/tanh in DOUBLE libm and rounds once, i.e. the
+// comparator is the correctly rounded fp32 value.  Arithmetic ops are written with explicit
+// round-to-nearest intrinsics so nvcc cannot contract them into FMAs: the x86-64 reference
+// has no FMA, and __fmul_rn/__fadd_rn make affine/axpby/hadamard BIT-EXACT with it.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/jz_b200.h"
+
+namespace jz {
+
+// s1*x + a, two roundings (cpp/core.hpp:452-469)
+__device__ __forceinline__ float affine_rn(float x, float s1, float a) {
+    return __fadd_rn(__fmul_rn(s1, x), a);
+}
+
+// l / x : the reference divides in double and rounds to float (cpp/core.hpp:471-482).
+// For fp32 operands double rounding of a quotient is innocuous (53 >= 2*24+2), so the
+// IEEE fp32 division gives the same bits.
+__device__ __forceinline__ float eleminv_rn(float x, float l) { return __fdiv_rn(l, x); }
+
+// d_tanh(x) = 1 - tanh(x)^2 = 4e / (1+e)^2 with e = exp(-2|x|).
+// The reference evaluates 1 - tanh^2 in double (cpp/matrix.hpp:301-324); in fp32 that form
+// cancels catastrophically for |x| >~ 5, so the quotient form is used with a compensated
+// denominator: s = fl(1+e) with exact residual serr (Fast2Sum, 1 >= e), t = fl(s*s) with exact
+// residual terr (FMA), and one correction step on the rounded quotient.
+__device__ __forceinline__ float dtanh_acc(float x) {
+    const float ax = fabsf(x);
+    const float e = expf(-2.0f * ax);
+    const float s = __fadd_rn(1.0f, e);
+    const float serr = __fsub_rn(e, __fsub_rn(s, 1.0f));
+    const float t = __fmul_rn(s, s);
+    const float terr = __fmaf_rn(s, s, -t);
+    const float c = __fmaf_rn(2.0f * s, serr, terr);  // (1+e)^2 = t + c (+ serr^2 ~ 2^-48)
+    const float num = 4.0f * e;
+    const float q0 = __fdiv_rn(num, t);
+    return __fmaf_rn(-q0, __fdividef(c, t), q0);
+}
+
+template <int OP>
+__device__ __forceinline__ float unary_op(float x) {
+    if constexpr (OP == JZ_EXP) return expf(x);
+    else if constexpr (OP == JZ_LOG) return logf(x);
+    else if constexpr (OP == JZ_TANH) return tanhf(x);
+    else if constexpr (OP == JZ_DTANH) return dtanh_acc(x);
+    else if constexpr (OP == JZ_SQUARE) return __fmul_rn(x, x);
+    else if constexpr (OP == JZ_SQRT) return __fsqrt_rn(x);
+    else if constexpr (OP == JZ_RELU) return x > 0.0f ? x : 0.0f;
+    else if constexpr (OP == JZ_DRELU) return x > 0.0f ? 1.0f : 0.0f;
+    else return x;
+}
+
+// runtime-dispatched step over a small register tile (switch amortised over N values)
+template <int N>
+__device__ __forceinline__ void apply_step(float (&v)[N], int kind, float s1, float a) {
+    switch (kind) {
+#define JZ_CASE(OP)                                         \
+    case OP:                                                \
+        _Pragma("unroll") for (int i = 0; i < N; i++) v[i] = unary_op<OP>(v[i]); \
+        break;
+        JZ_CASE(JZ_EXP)
+        JZ_CASE(JZ_LOG)
+        JZ_CASE(JZ_TANH)
+        JZ_CASE(JZ_DTANH)
+        JZ_CASE(JZ_SQUARE)
+        JZ_CASE(JZ_SQRT)
+        JZ_CASE(JZ_RELU)
+        JZ_CASE(JZ_DRELU)
+#undef JZ_CASE
+        case JZ_STEP_AFFINE:
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = affine_rn(v[i], s1, a);
+            break;
+        case JZ_STEP_ELEMINV:
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = eleminv_rn(v[i], s1);
+            break;
+        default: break;
+    }
+}
+
+struct ChainParams {
+    int n;
+    int kind[JZ_MAX_CHAIN];
+    float s1[JZ_MAX_CHAIN];
+    float a[JZ_MAX_CHAIN];
+};
+
+template <int N>
+__device__ __forceinline__ void apply_chain(float (&v)[N], const ChainParams& c) {
+    for (int s = 0; s < c.n; s++) apply_step<N>(v, c.kind[s], c.s1[s], c.a[s]);
+}
+
+inline int make_chain(ChainParams& c, const jz_step* steps, int nsteps) {
+    if (nsteps < 0 || nsteps > JZ_MAX_CHAIN || (nsteps > 0 && !steps)) return JZ_ERR_ARG;
+    c.n = nsteps;
+    for (int i = 0; i < nsteps; i++) {
+        const int k = steps[i].kind;
+        if (!((k >= 0 && k < JZ_UNARY_COUNT) || k == JZ_STEP_AFFINE || k == JZ_STEP_ELEMINV)) return JZ_ERR_ARG;
+        c.kind[i] = k;
+        c.s1[i] = steps[i].s1;
+        c.a[i] = steps[i].a;
+    }
+    return JZ_OK;
+}
+
+}  // namespace jz

@@ -1,0 +1,526 @@
+// jz_reduce.cu -- row / column reductions (SURVEY 8a rows a11 sum, a12 max-reduce,
+// a13 softmax composite, a18 norm).  Algorithmic traffic: 4 B/elem read (+4 B per output),
+// column softmax 8 B/elem.
+//
+// The reference reaches these through cublasSgemv with a freshly filled ones vector (3 fill
+// launches + gemv, cpp/cumatrix.cu:312-337), a one-thread-per-column serial functor kernel
+// with stride-`rows` (uncoalesced) accesses (cpp/cumatrix.cuh:334-384) and ~10 kernels + 2
+// rank-1 GEMMs for the softmax (ml/layer.hpp:252-283).  Here every variant is one or two
+// coalesced streaming passes, chosen by shape:
+//
+//  dim 0 (reduce down each contiguous column):
+//    rows <= 32      : a CTA stages 256 columns (one contiguous span) in shared memory with
+//                      128-bit loads, then one thread reduces one column from a skewed,
+//                      bank-conflict-free layout;
+//    otherwise       : one warp per column (128-bit loads, 4 accumulators per lane, shuffle
+//                      tree), or, for few very long columns, (chunk x column) CTAs writing
+//                      partials that a second tiny pass folds -- no atomics, so results are
+//                      deterministic for a given shape.
+//  dim 1 (reduce across columns, i.e. add the columns into a vector):
+//    each thread owns 4 consecutive rows (float4) and walks columns; the columns are split
+//    across threadIdx.y and across CTAs (grid.y); CTAs write per-chunk partial vectors which
+//    a second pass folds.  Every global read is a full coalesced row segment.
+#include <cfloat>
+#include <type_traits>
+
+#include "jz_common.cuh"
+#include "jz_math.cuh"
+
+namespace jz {
+
+struct SumOp {
+    static __device__ __forceinline__ float init() { return 0.0f; }
+    static __device__ __forceinline__ float apply(float a, float b) { return __fadd_rn(a, b); }
+};
+struct MaxOp {  // the LogisticLayer column-max functor: m = -1e30f; m = m > v ? m : v
+    static __device__ __forceinline__ float init() { return -1e30f; }
+    static __device__ __forceinline__ float apply(float a, float b) { return a > b ? a : b; }
+};
+
+template <class Op>
+__device__ __forceinline__ float warp_reduce(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = Op::apply(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------ dim 0, short columns
+constexpr int kShortCols = 256;  // columns per CTA
+constexpr int kShortMaxRows = 32;
+
+__device__ __forceinline__ int skew(int e) { return e + (e >> 5); }
+
+// stage `ncols` columns of `rows` floats (column c at a + c*ld) into skewed smem
+__device__ __forceinline__ void stage_columns(float* sm, const float* a, size_t ld, int rows, int ncols,
+                                              bool contiguous_vec) {
+    const int total = rows * ncols;
+    if (contiguous_vec) {  // ld == rows, base 16B aligned, span is one contiguous run
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const int total4 = total >> 2;
+        for (int e4 = threadIdx.x; e4 < total4; e4 += blockDim.x) {
+            const float4 v = a4[e4];
+            const int e = e4 << 2;
+            sm[skew(e)] = v.x; sm[skew(e + 1)] = v.y; sm[skew(e + 2)] = v.z; sm[skew(e + 3)] = v.w;
+        }
+        for (int e = (total4 << 2) + threadIdx.x; e < total; e += blockDim.x) sm[skew(e)] = a[e];
+    } else {
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            const int c = e / rows, r = e - c * rows;
+            sm[skew(e)] = a[size_t(c) * ld + r];
+        }
+    }
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kShortCols) colreduce_short_kernel(float* out, const float* a, int rows,
+                                                                     size_t cols, size_t ld, bool vec) {
+    extern __shared__ float sm[];
+    for (size_t c0 = size_t(blockIdx.x) * kShortCols; c0 < cols; c0 += size_t(gridDim.x) * kShortCols) {
+        const int ncols = int(cols - c0 < size_t(kShortCols) ? cols - c0 : kShortCols);
+        stage_columns(sm, a + c0 * ld, ld, rows, ncols, vec);
+        __syncthreads();
+        if (int(threadIdx.x) < ncols) {
+            float acc = Op::init();
+            const int base = threadIdx.x * rows;
+            for (int r = 0; r < rows; r++) acc = Op::apply(acc, sm[skew(base + r)]);  // serial, reference order
+            out[c0 + threadIdx.x] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// column softmax for short columns: exact reference order inside a column
+// mode 0: out = softmax ; mode 1: out = -(y - softmax)/nb evaluated as the operators do
+__global__ void __launch_bounds__(kShortCols) softmax_short_kernel(float* out, const float* a, const float* y,
+                                                                   int rows, size_t cols, size_t ld, bool vec,
+                                                                   int mode, float rnb) {
+    extern __shared__ float sm[];
+    for (size_t c0 = size_t(blockIdx.x) * kShortCols; c0 < cols; c0 += size_t(gridDim.x) * kShortCols) {
+        const int ncols = int(cols - c0 < size_t(kShortCols) ? cols - c0 : kShortCols);
+        stage_columns(sm, a + c0 * ld, ld, rows, ncols, vec);
+        __syncthreads();
+        if (int(threadIdx.x) < ncols) {
+            const int base = threadIdx.x * rows;
+            float m = -1e30f;
+            for (int r = 0; r < rows; r++) { const float v = sm[skew(base + r)]; m = m > v ? m : v; }
+            float z = 0.0f;
+            for (int r = 0; r < rows; r++) {
+                const float e = expf(__fadd_rn(-m, sm[skew(base + r)]));
+                sm[skew(base + r)] = e;
+                z = __fadd_rn(z, e);
+            }
+            const float inv = __fdiv_rn(1.0f, z);
+            for (int r = 0; r < rows; r++) sm[skew(base + r)] = __fmul_rn(sm[skew(base + r)], inv);
+        }
+        __syncthreads();
+        // coalesced write-back (out is contiguous rows x cols, ld == rows)
+        const int total = rows * ncols;
+        float* o = out + c0 * size_t(rows);
+        const float* yy = y ? y + c0 * size_t(rows) : nullptr;
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            float s = sm[skew(e)];
+            if (mode == 1) {
+                const float d = __fadd_rn(-s, yy[e]);          // rM.add(lM,-1,1): -1*S + 1*Y
+                const float neg = __fadd_rn(-d, 0.0f);         // unary minus: -1*d + 0
+                s = __fadd_rn(__fmul_rn(rnb, neg), 0.0f);      // /nb: (float)(1/nb)*x + 0
+            }
+            o[e] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ dim 0, warp per column
+template <class Op, bool VEC>
+__device__ __forceinline__ float lane_reduce_span(const float* col, size_t len, int lane) {
+    float a0 = Op::init(), a1 = Op::init(), a2 = Op::init(), a3 = Op::init();
+    if (VEC) {
+        const float4* c4 = reinterpret_cast<const float4*>(col);
+        const size_t n4 = len >> 2;
+        size_t i = lane;
+        for (; i + 96 < n4; i += 128) {
+            const float4 v0 = c4[i], v1 = c4[i + 32], v2 = c4[i + 64], v3 = c4[i + 96];
+            a0 = Op::apply(a0, Op::apply(Op::apply(v0.x, v0.y), Op::apply(v0.z, v0.w)));
+            a1 = Op::apply(a1, Op::apply(Op::apply(v1.x, v1.y), Op::apply(v1.z, v1.w)));
+            a2 = Op::apply(a2, Op::apply(Op::apply(v2.x, v2.y), Op::apply(v2.z, v2.w)));
+            a3 = Op::apply(a3, Op::apply(Op::apply(v3.x, v3.y), Op::apply(v3.z, v3.w)));
+        }
+        for (; i < n4; i += 32) {
+            const float4 v0 = c4[i];
+            a0 = Op::apply(a0, Op::apply(Op::apply(v0.x, v0.y), Op::apply(v0.z, v0.w)));
+        }
+        for (size_t t = (n4 << 2) + lane; t < len; t += 32) a1 = Op::apply(a1, col[t]);
+    } else {
+        size_t i = lane;
+        for (; i + 96 < len; i += 128) {
+            a0 = Op::apply(a0, col[i]);
+            a1 = Op::apply(a1, col[i + 32]);
+            a2 = Op::apply(a2, col[i + 64]);
+            a3 = Op::apply(a3, col[i + 96]);
+        }
+        for (; i < len; i += 32) a0 = Op::apply(a0, col[i]);
+    }
+    return Op::apply(Op::apply(a0, a1), Op::apply(a2, a3));
+}
+
+template <class Op, bool VEC>
+__global__ void __launch_bounds__(256) colreduce_warp_kernel(float* out, const float* a, size_t rows, size_t cols,
+                                                             size_t ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (size_t c = size_t(blockIdx.x) * 8 + warp; c < cols; c += size_t(gridDim.x) * 8) {
+        float v = lane_reduce_span<Op, VEC>(a + c * ld, rows, lane);
+        v = warp_reduce<Op>(v);
+        if (lane == 0) out[c] = v;
+    }
+}
+
+// few, very long columns: CTA (chunk, column) -> partial[column * nchunks + chunk]
+template <class Op, bool VEC>
+__global__ void __launch_bounds__(256) colreduce_chunk_kernel(float* partial, const float* a, size_t rows,
+                                                              size_t ld, size_t chunk_len, unsigned nchunks) {
+    __shared__ float ws[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t c = blockIdx.y;
+    const size_t begin = size_t(blockIdx.x) * chunk_len;
+    const size_t end = begin + chunk_len < rows ? begin + chunk_len : rows;
+    // each warp takes a contiguous eighth of the chunk (multiple of 4 elements keeps float4 alignment)
+    const size_t len = end > begin ? end - begin : 0;
+    size_t per = ((len + 7) / 8 + 3) & ~size_t(3);
+    size_t wb = begin + size_t(warp) * per;
+    size_t we = wb + per < end ? wb + per : end;
+    float v = Op::init();
+    if (wb < we) v = lane_reduce_span<Op, VEC>(a + c * ld + wb, we - wb, lane);
+    v = warp_reduce<Op>(v);
+    if (lane == 0) ws[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < 8 ? ws[lane] : Op::init();
+        t = warp_reduce<Op>(t);
+        if (lane == 0) partial[c * nchunks + blockIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------ dim 1 (across columns)
+// block (tx, ty); thread owns VEC rows; columns [j_begin, j_end) of this CTA's chunk are strided over ty.
+template <class Op, int VEC>
+__global__ void __launch_bounds__(256) rowreduce_kernel(float* out /* nchunks x rows */, const float* a, size_t rows,
+                                                        size_t cols, size_t ld, size_t cols_per_chunk) {
+    extern __shared__ float sm[];  // ty x (tx*VEC)
+    const size_t row_units = rows / VEC;
+    const size_t iu = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t j_begin = size_t(blockIdx.y) * cols_per_chunk;
+    const size_t j_end = j_begin + cols_per_chunk < cols ? j_begin + cols_per_chunk : cols;
+    float acc[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; q++) acc[q] = Op::init();
+    if (iu < row_units) {
+        const float* base = a + iu * VEC;
+        size_t j = j_begin + threadIdx.y;
+        const size_t step = blockDim.y;
+        if constexpr (VEC == 4) {
+            float4 b0 = make_float4(Op::init(), Op::init(), Op::init(), Op::init()), b1 = b0, b2 = b0, b3 = b0;
+            for (; j + 3 * step < j_end; j += 4 * step) {
+                const float4 v0 = *reinterpret_cast<const float4*>(base + j * ld);
+                const float4 v1 = *reinterpret_cast<const float4*>(base + (j + step) * ld);
+                const float4 v2 = *reinterpret_cast<const float4*>(base + (j + 2 * step) * ld);
+                const float4 v3 = *reinterpret_cast<const float4*>(base + (j + 3 * step) * ld);
+                b0.x = Op::apply(b0.x, v0.x); b0.y = Op::apply(b0.y, v0.y); b0.z = Op::apply(b0.z, v0.z); b0.w = Op::apply(b0.w, v0.w);
+                b1.x = Op::apply(b1.x, v1.x); b1.y = Op::apply(b1.y, v1.y); b1.z = Op::apply(b1.z, v1.z); b1.w = Op::apply(b1.w, v1.w);
+                b2.x = Op::apply(b2.x, v2.x); b2.y = Op::apply(b2.y, v2.y); b2.z = Op::apply(b2.z, v2.z); b2.w = Op::apply(b2.w, v2.w);
+                b3.x = Op::apply(b3.x, v3.x); b3.y = Op::apply(b3.y, v3.y); b3.z = Op::apply(b3.z, v3.z); b3.w = Op::apply(b3.w, v3.w);
+            }
+            for (; j < j_end; j += step) {
+                const float4 v0 = *reinterpret_cast<const float4*>(base + j * ld);
+                b0.x = Op::apply(b0.x, v0.x); b0.y = Op::apply(b0.y, v0.y); b0.z = Op::apply(b0.z, v0.z); b0.w = Op::apply(b0.w, v0.w);
+            }
+            acc[0] = Op::apply(Op::apply(b0.x, b1.x), Op::apply(b2.x, b3.x));
+            acc[1 % VEC] = Op::apply(Op::apply(b0.y, b1.y), Op::apply(b2.y, b3.y));
+            acc[2 % VEC] = Op::apply(Op::apply(b0.z, b1.z), Op::apply(b2.z, b3.z));
+            acc[3 % VEC] = Op::apply(Op::apply(b0.w, b1.w), Op::apply(b2.w, b3.w));
+        } else {
+            float b0 = Op::init(), b1 = b0, b2 = b0, b3 = b0;
+            for (; j + 3 * step < j_end; j += 4 * step) {
+                b0 = Op::apply(b0, base[j * ld]);
+                b1 = Op::apply(b1, base[(j + step) * ld]);
+                b2 = Op::apply(b2, base[(j + 2 * step) * ld]);
+                b3 = Op::apply(b3, base[(j + 3 * step) * ld]);
+            }
+            for (; j < j_end; j += step) b0 = Op::apply(b0, base[j * ld]);
+            acc[0] = Op::apply(Op::apply(b0, b1), Op::apply(b2, b3));
+        }
+    }
+    // fold threadIdx.y in shared memory
+    const int width = blockDim.x * VEC;
+#pragma unroll
+    for (int q = 0; q < VEC; q++) sm[threadIdx.y * width + threadIdx.x * VEC + q] = acc[q];
+    __syncthreads();
+    for (int e = threadIdx.y * blockDim.x + threadIdx.x; e < width; e += blockDim.x * blockDim.y) {
+        float t = Op::init();
+        for (int yy = 0; yy < int(blockDim.y); yy++) t = Op::apply(t, sm[yy * width + e]);
+        const size_t row = size_t(blockIdx.x) * width + e;
+        if (row < rows) out[size_t(blockIdx.y) * rows + row] = t;
+    }
+}
+
+// ------------------------------------------------------------------ long-column softmax (warp per column)
+template <bool VEC>
+__global__ void __launch_bounds__(256) softmax_warp_kernel(float* out, const float* a, size_t rows, size_t cols,
+                                                           size_t ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (size_t c = size_t(blockIdx.x) * 8 + warp; c < cols; c += size_t(gridDim.x) * 8) {
+        const float* col = a + c * ld;
+        float* o = out + c * rows;
+        float m = warp_reduce<MaxOp>(lane_reduce_span<MaxOp, VEC>(col, rows, lane));
+        float z = 0.0f;
+        for (size_t i = lane; i < rows; i += 32) {
+            const float e = expf(__fadd_rn(-m, col[i]));
+            o[i] = e;
+            z += e;
+        }
+        z = warp_reduce<SumOp>(z);
+        const float inv = __fdiv_rn(1.0f, z);
+        for (size_t i = lane; i < rows; i += 32) o[i] = __fmul_rn(o[i], inv);  // same lane re-reads its own writes
+    }
+}
+
+struct CeGradF {
+    float rnb;
+    __device__ __forceinline__ float operator()(float s, float y) const {
+        const float d = __fadd_rn(-s, y);
+        const float neg = __fadd_rn(-d, 0.0f);
+        return __fadd_rn(__fmul_rn(rnb, neg), 0.0f);
+    }
+};
+template <class F>
+__global__ void __launch_bounds__(256) map2_inplace_kernel(float* out, const float* b, size_t n, F f) {
+    for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += size_t(gridDim.x) * 256) out[i] = f(out[i], b[i]);
+}
+
+// ------------------------------------------------------------------ nrm2
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(double* partial, const float* x, size_t n, bool vec) {
+    __shared__ double ws[8];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    double acc = 0.0;
+    const size_t stride = size_t(gridDim.x) * 256;
+    if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const size_t n4 = n >> 2;
+        int flush = 0;
+        for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < n4; i += stride) {
+            const float4 v = x4[i];
+            a0 = fmaf(v.x, v.x, a0); a1 = fmaf(v.y, v.y, a1); a2 = fmaf(v.z, v.z, a2); a3 = fmaf(v.w, v.w, a3);
+            if (++flush == 64) { acc += double(a0) + double(a1) + double(a2) + double(a3); a0 = a1 = a2 = a3 = 0.f; flush = 0; }
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float t = x[(n4 << 2) + threadIdx.x]; a0 = fmaf(t, t, a0); }
+    } else {
+        int flush = 0;
+        for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) {
+            const float t = x[i];
+            a0 = fmaf(t, t, a0);
+            if (++flush == 256) { acc += double(a0); a0 = 0.f; flush = 0; }
+        }
+    }
+    acc += double(a0) + double(a1) + double(a2) + double(a3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += ws[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void nrm2_final_kernel(float* out, const double* partial, int n) {
+    __shared__ double ws[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < int(blockDim.x >> 5); w++) t += ws[w];
+        out[0] = float(sqrt(t));
+    }
+}
+
+// ------------------------------------------------------------------ host dispatch
+template <class Op>
+static int reduce_dim1(float* out, const float* a, size_t rows, size_t cols, size_t ld, cudaStream_t s);
+
+template <class Op>
+static int reduce_dim0(float* out, const float* a, size_t rows, size_t cols, size_t ld, cudaStream_t s) {
+    const size_t cap = size_t(ctx().sm_count) * 8;
+    if (rows <= size_t(kShortMaxRows)) {
+        const bool vec = (ld == rows) && aligned16(a);
+        const size_t blocks = ceil_div(cols, size_t(kShortCols));
+        const size_t bytes = (size_t(kShortCols) * rows + (size_t(kShortCols) * rows) / 32 + 2) * sizeof(float);
+        JZ_LAUNCH((colreduce_short_kernel<Op>), unsigned(blocks < cap ? blocks : cap), kShortCols, bytes, s, out, a,
+                  int(rows), cols, ld, vec);
+        return JZ_OK;
+    }
+    const bool vec = aligned16(a) && ld % 4 == 0;
+    const size_t warps_wanted = cap * 8;  // one full wave of warps
+    if (cols * 4 >= warps_wanted || rows < 32768) {
+        const size_t blocks = ceil_div(cols, size_t(8));
+        const unsigned grid = unsigned(blocks < cap ? blocks : cap);
+        if (vec) JZ_LAUNCH((colreduce_warp_kernel<Op, true>), grid, 256, 0, s, out, a, rows, cols, ld);
+        else JZ_LAUNCH((colreduce_warp_kernel<Op, false>), grid, 256, 0, s, out, a, rows, cols, ld);
+        return JZ_OK;
+    }
+    // few long columns: split rows into chunks so that ~2 waves of CTAs exist
+    size_t nchunks = ceil_div(2 * cap, cols);
+    size_t chunk_len = ceil_div(rows, nchunks);
+    if (chunk_len < 8192) chunk_len = 8192;
+    chunk_len = (chunk_len + 31) & ~size_t(31);
+    nchunks = ceil_div(rows, chunk_len);
+    if (cols > 65535) return fail(JZ_ERR_UNSUPPORTED, "reduce: too many long columns");
+    void* partial = nullptr;
+    int rc = ws_alloc(&partial, nchunks * cols * sizeof(float), s);
+    if (rc != JZ_OK) return rc;
+    float* pf = static_cast<float*>(partial);
+    const dim3 grid((unsigned)nchunks, (unsigned)cols, 1);
+    if (vec) JZ_LAUNCH((colreduce_chunk_kernel<Op, true>), grid, 256, 0, s, pf, a, rows, ld, chunk_len, unsigned(nchunks));
+    else JZ_LAUNCH((colreduce_chunk_kernel<Op, false>), grid, 256, 0, s, pf, a, rows, ld, chunk_len, unsigned(nchunks));
+    // fold: partial is an (nchunks x cols) col-major matrix -> reduce down its columns
+    rc = reduce_dim0<Op>(out, pf, nchunks, cols, nchunks, s);
+    ws_free(partial, s);
+    return rc;
+}
+
+template <class Op>
+static int reduce_dim1(float* out, const float* a, size_t rows, size_t cols, size_t ld, cudaStream_t s) {
+    const size_t cap = size_t(ctx().sm_count) * 8;
+    const bool vec = aligned16(a) && ld % 4 == 0 && rows % 4 == 0;
+    const int V = vec ? 4 : 1;
+    const size_t row_units = rows / V;
+    unsigned tx = 1;
+    while (tx < 256 && tx < row_units) tx <<= 1;
+    if (tx > 64 && vec) tx = 64;  // keep >= 4 column phases per CTA for MLP
+    const unsigned ty = 256 / tx;
+    const size_t gx = ceil_div(row_units, tx);
+    // split columns into chunks so the grid has ~2 waves, but keep >= 8*ty columns per chunk
+    size_t nchunks = ceil_div(2 * cap, gx);
+    const size_t min_cols = size_t(ty) * 8;
+    if (nchunks * min_cols > cols) nchunks = cols / min_cols;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 65535) nchunks = 65535;
+    const size_t cpc = ceil_div(cols, nchunks);
+    nchunks = ceil_div(cols, cpc);
+    const size_t smem = size_t(ty) * tx * V * sizeof(float);
+    const dim3 grid((unsigned)gx, (unsigned)nchunks, 1), block(tx, ty, 1);
+    float* dst = out;
+    void* partial = nullptr;
+    if (nchunks > 1) {
+        int rc = ws_alloc(&partial, nchunks * rows * sizeof(float), s);
+        if (rc != JZ_OK) return rc;
+        dst = static_cast<float*>(partial);
+    }
+    if (vec) JZ_LAUNCH((rowreduce_kernel<Op, 4>), grid, block, smem, s, dst, a, rows, cols, ld, cpc);
+    else JZ_LAUNCH((rowreduce_kernel<Op, 1>), grid, block, smem, s, dst, a, rows, cols, ld, cpc);
+    if (nchunks > 1) {
+        // partial is rows x nchunks (col-major, ld = rows): fold across its columns
+        int rc = reduce_dim1<Op>(out, dst, rows, nchunks, rows, s);
+        ws_free(partial, s);
+        return rc;
+    }
+    return JZ_OK;
+}
+
+template <class Op>
+static int reduce_entry(float* out, const float* a, size_t rows, size_t cols, size_t ld, int dim, cudaStream_t s) {
+    if (dim != 0 && dim != 1) return fail(JZ_ERR_ARG, "reduce: dim must be 0 or 1");
+    if (ld < rows) return fail(JZ_ERR_SHAPE, "reduce: ld < rows");
+    const size_t nout = dim == 0 ? cols : rows;
+    if (nout == 0) return JZ_OK;
+    if (!out || (!a && rows * cols)) return fail(JZ_ERR_ARG, "reduce: null pointer");
+    if ((dim == 0 ? rows : cols) == 0) {  // empty reduction: identity
+        float init = 0.0f;
+        if (std::is_same<Op, MaxOp>::value) init = -1e30f;
+        return jz_fill(out, nout, init, s);
+    }
+    return dim == 0 ? reduce_dim0<Op>(out, a, rows, cols, ld, s) : reduce_dim1<Op>(out, a, rows, cols, ld, s);
+}
+
+}  // namespace jz
+
+using namespace jz;
+
+extern "C" {
+
+int jz_sum(float* out, const float* a, size_t rows, size_t cols, size_t ld, int dim, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    return reduce_entry<SumOp>(out, a, rows, cols, ld, dim, as_stream(stream));
+}
+
+int jz_max(float* out, const float* a, size_t rows, size_t cols, size_t ld, int dim, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    return reduce_entry<MaxOp>(out, a, rows, cols, ld, dim, as_stream(stream));
+}
+
+static int softmax_impl(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode,
+                        float rnb, cudaStream_t s) {
+    if (rows == 0 || cols == 0) return JZ_OK;
+    if (!out || !a || (mode == 1 && !y)) return fail(JZ_ERR_ARG, "softmax: null pointer");
+    if (ld < rows) return fail(JZ_ERR_SHAPE, "softmax: ld < rows");
+    const size_t cap = size_t(ctx().sm_count) * 8;
+    if (rows <= size_t(kShortMaxRows)) {
+        const bool vec = (ld == rows) && aligned16(a);
+        const size_t blocks = ceil_div(cols, size_t(kShortCols));
+        const size_t bytes = (size_t(kShortCols) * rows + (size_t(kShortCols) * rows) / 32 + 2) * sizeof(float);
+        JZ_LAUNCH(softmax_short_kernel, unsigned(blocks < cap ? blocks : cap), kShortCols, bytes, s, out, a, y, int(rows),
+                  cols, ld, vec, mode, rnb);
+        return JZ_OK;
+    }
+    const bool vec = aligned16(a) && ld % 4 == 0;
+    const size_t blocks = ceil_div(cols, size_t(8));
+    const unsigned grid = unsigned(blocks < cap ? blocks : cap);
+    if (vec) JZ_LAUNCH((softmax_warp_kernel<true>), grid, 256, 0, s, out, a, rows, cols, ld);
+    else JZ_LAUNCH((softmax_warp_kernel<false>), grid, 256, 0, s, out, a, rows, cols, ld);
+    if (mode == 1) {
+        const size_t n = rows * cols;
+        const size_t b2 = ceil_div(n, size_t(1024));
+        JZ_LAUNCH((map2_inplace_kernel<CeGradF>), unsigned(b2 < cap ? b2 : cap), 256, 0, s, out, y, n, CeGradF{rnb});
+    }
+    return JZ_OK;
+}
+
+int jz_softmax_cols(float* out, const float* a, size_t rows, size_t cols, size_t ld, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    return softmax_impl(out, a, nullptr, rows, cols, ld, 0, 0.0f, as_stream(stream));
+}
+
+int jz_softmax_ce_grad(float* out, const float* x, const float* y, size_t rows, size_t cols, float nb,
+                       jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    const float rnb = float(1.0 / double(nb));  // operator/ : scale((float)(1.0/r)), cpp/operators.hpp:236-246
+    return softmax_impl(out, x, y, rows, cols, rows, 1, rnb, as_stream(stream));
+}
+
+int jz_nrm2(const float* x, size_t n, float* result_host, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    if (!result_host) return fail(JZ_ERR_ARG, "jz_nrm2: null result pointer");
+    if (n == 0) { *result_host = 0.0f; return JZ_OK; }
+    if (!x) return fail(JZ_ERR_ARG, "jz_nrm2: null pointer");
+    cudaStream_t s = as_stream(stream);
+    const size_t cap = size_t(ctx().sm_count) * 4;
+    const bool vec = aligned16(x);
+    const size_t want = ceil_div(vec ? (n >> 2) + 1 : n, size_t(256) * 4);
+    const unsigned grid = unsigned(want < cap ? (want ? want : 1) : cap);
+    void* ws = nullptr;
+    int rc = ws_alloc(&ws, grid * sizeof(double) + 16, s);
+    if (rc != JZ_OK) return rc;
+    double* partial = static_cast<double*>(ws);
+    float* dres = reinterpret_cast<float*>(partial + grid);
+    JZ_LAUNCH(sumsq_partial_kernel, grid, 256, 0, s, partial, x, n, vec);
+    JZ_LAUNCH(nrm2_final_kernel, 1, 256, 0, s, dres, partial, int(grid));
+    JZ_CUDA(cudaMemcpyAsync(result_host, dres, sizeof(float), cudaMemcpyDeviceToHost, s));
+    JZ_CUDA(cudaStreamSynchronize(s));
+    ws_free(ws, s);
+    return JZ_OK;
+}
+
+}  // extern "C"

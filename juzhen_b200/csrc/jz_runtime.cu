@@ -1,0 +1,299 @@
+// jz_runtime.cu -- lifetime, error reporting, copies and the stream-ordered pool.
+//
+// Replaces the reference's process-scope setup (cpp/launcher.cu:44-101: cuBLAS handle +
+// RAII Memory<CUDAfloat>) and its exact-size free-list pool (cpp/memory.hpp:50-119 over
+// cudaMalloc/cudaFree, cpp/cumatrix.cuh:67-85).
+//
+// Pool design (B200: 180 GB HBM3e, cudaMalloc is ~100 us-1 ms so temporaries must never
+// reach the driver in steady state):
+//   * sizes are rounded to 512 B; a freed block goes to a per-size free list (the
+//     reference's "exact size match" rule, which is what makes rvalue chains hit).
+//   * STREAM-ORDERED: a block remembers the stream it was freed on.  Re-allocation on the
+//     same stream is immediate (program order on the stream protects it); re-allocation
+//     on a different stream first makes that stream wait on an event recorded on the
+//     freeing stream, so no host synchronisation is ever needed.
+//   * on cudaMalloc failure the cached blocks are released to the driver and the
+//     allocation retried once (the reference never trims; with 4 GiB temporaries at
+//     32768^2 that matters).
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "jz_common.cuh"
+
+namespace jz {
+
+static Ctx g_ctx;
+static thread_local char g_err[512] = "";
+
+Ctx& ctx() { return g_ctx; }
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(e == cudaErrorMemoryAllocation ? JZ_ERR_OOM : JZ_ERR_CUDA, "CUDA error: %s (%s)",
+                cudaGetErrorString(e), what);
+}
+
+static std::mutex g_init_mu;
+
+static int do_init(int device) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (g_ctx.inited && (device < 0 || device == g_ctx.device)) return JZ_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(JZ_ERR_CUDA,
+                    "no CUDA device available (%s): libjz_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) return fail(JZ_ERR_ARG, "device %d out of range (%d devices)", device, count);
+    JZ_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    JZ_CUDA(cudaGetDeviceProperties(&p, device));
+    g_ctx.device = device;
+    g_ctx.sm_count = p.multiProcessorCount;
+    g_ctx.cc_major = p.major;
+    g_ctx.cc_minor = p.minor;
+    g_ctx.total_mem = p.totalGlobalMem;
+    // GEMM mode: NVIDIA_TF32=1 keeps the reference's spelling (cpp/launcher.cu:73-77)
+    const char* tf32 = std::getenv("NVIDIA_TF32");
+    if (tf32 && *tf32 && std::strcmp(tf32, "0") != 0) g_ctx.gemm_mode = JZ_GEMM_TF32;
+    const char* gm = std::getenv("JZ_GEMM_MODE");
+    if (gm && *gm) {
+        if (!std::strcmp(gm, "3xtf32")) g_ctx.gemm_mode = JZ_GEMM_3XTF32;
+        else if (!std::strcmp(gm, "tf32")) g_ctx.gemm_mode = JZ_GEMM_TF32;
+        else if (!std::strcmp(gm, "fp32")) g_ctx.gemm_mode = JZ_GEMM_FP32_SIMT;
+        else if (!std::strcmp(gm, "bf16")) g_ctx.gemm_mode = JZ_GEMM_BF16;
+    }
+    g_ctx.inited = true;
+    return JZ_OK;
+}
+
+int ensure_init() {
+    if (g_ctx.inited) return JZ_OK;
+    return do_init(-1);
+}
+
+// ------------------------------------------------------------------ pool
+struct Block {
+    void* ptr;
+    size_t bytes;
+    cudaStream_t freed_on;
+};
+
+struct Pool {
+    std::mutex mu;
+    std::unordered_map<void*, size_t> live;                 // ptr -> rounded bytes
+    std::unordered_map<size_t, std::vector<Block>> cached;  // rounded bytes -> free blocks
+    std::vector<cudaEvent_t> events;                        // recycled events
+    size_t live_bytes = 0, cached_bytes = 0, n_device_allocs = 0, n_hits = 0;
+
+    static size_t round_up(size_t bytes) {
+        if (bytes == 0) bytes = 4;  // count==0 -> 1 element (cpp/cumatrix.cuh:71)
+        return (bytes + 511) & ~size_t(511);
+    }
+
+    int trim_locked() {
+        for (auto& kv : cached)
+            for (auto& b : kv.second) cudaFree(b.ptr);
+        cached.clear();
+        cached_bytes = 0;
+        return JZ_OK;
+    }
+
+    int alloc(void** out, size_t bytes, cudaStream_t s) {
+        const size_t rb = round_up(bytes);
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cached.find(rb);
+        if (it != cached.end() && !it->second.empty()) {
+            // prefer a block freed on the same stream (no cross-stream wait needed)
+            auto& vec = it->second;
+            size_t pick = vec.size() - 1;
+            for (size_t i = vec.size(); i-- > 0;)
+                if (vec[i].freed_on == s) { pick = i; break; }
+            Block b = vec[pick];
+            vec.erase(vec.begin() + pick);
+            if (b.freed_on != s) {
+                cudaEvent_t ev;
+                if (!events.empty()) { ev = events.back(); events.pop_back(); }
+                else JZ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                JZ_CUDA(cudaEventRecord(ev, b.freed_on));
+                JZ_CUDA(cudaStreamWaitEvent(s, ev, 0));
+                events.push_back(ev);
+            }
+            cached_bytes -= rb;
+            live_bytes += rb;
+            live.emplace(b.ptr, rb);
+            n_hits++;
+            *out = b.ptr;
+            return JZ_OK;
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, rb);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaDeviceSynchronize();
+            trim_locked();
+            e = cudaMalloc(&p, rb);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(JZ_ERR_OOM, "device allocation of %zu bytes failed (%s); live %zu bytes",
+                            rb, cudaGetErrorString(e), live_bytes);
+            }
+        }
+        n_device_allocs++;
+        live_bytes += rb;
+        live.emplace(p, rb);
+        *out = p;
+        return JZ_OK;
+    }
+
+    int release(void* p, cudaStream_t s) {
+        if (!p) return JZ_OK;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = live.find(p);
+        if (it == live.end())
+            return fail(JZ_ERR_ARG, "jz_free: pointer %p is not a live pool allocation", p);
+        const size_t rb = it->second;
+        live.erase(it);
+        live_bytes -= rb;
+        cached_bytes += rb;
+        cached[rb].push_back(Block{p, rb, s});
+        return JZ_OK;
+    }
+
+    int destroy() {
+        std::lock_guard<std::mutex> lk(mu);
+        cudaDeviceSynchronize();
+        trim_locked();
+        for (auto& kv : live) cudaFree(kv.first);
+        live.clear();
+        live_bytes = 0;
+        for (auto ev : events) cudaEventDestroy(ev);
+        events.clear();
+        return JZ_OK;
+    }
+};
+
+static Pool& pool() {
+    static Pool* p = new Pool();  // intentionally leaked: outlives static destructors of callers
+    return *p;
+}
+
+int ws_alloc(void** p, size_t bytes, cudaStream_t s) { return pool().alloc(p, bytes, s); }
+int ws_free(void* p, cudaStream_t s) { return pool().release(p, s); }
+
+}  // namespace jz
+
+using namespace jz;
+
+extern "C" {
+
+int jz_abi_version(void) { return JZ_ABI_VERSION; }
+
+int jz_init(int device) { return do_init(device); }
+
+int jz_shutdown(void) {
+    if (!g_ctx.inited) return JZ_OK;
+    pool().destroy();
+    g_ctx.inited = false;
+    return JZ_OK;
+}
+
+const char* jz_last_error(void) { return g_err; }
+
+int jz_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+    JZ_INIT_OR_RETURN();
+    if (sm_count) *sm_count = g_ctx.sm_count;
+    if (cc_major) *cc_major = g_ctx.cc_major;
+    if (cc_minor) *cc_minor = g_ctx.cc_minor;
+    if (total_mem) *total_mem = g_ctx.total_mem;
+    return JZ_OK;
+}
+
+int jz_sync(jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    JZ_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return JZ_OK;
+}
+
+uint64_t jz_launch_count(void) { return g_ctx.launches.load(); }
+
+int jz_set_gemm_mode(int mode) {
+    if (mode < JZ_GEMM_3XTF32 || mode > JZ_GEMM_BF16) return fail(JZ_ERR_ARG, "bad gemm mode %d", mode);
+    g_ctx.gemm_mode = mode;
+    return JZ_OK;
+}
+int jz_get_gemm_mode(void) { return g_ctx.gemm_mode; }
+int jz_gemm_last_path(void) { return g_ctx.gemm_last_path; }
+
+int jz_malloc(float** ptr, size_t count, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    if (!ptr) return fail(JZ_ERR_ARG, "jz_malloc: null out pointer");
+    void* p = nullptr;
+    int rc = pool().alloc(&p, count * sizeof(float), as_stream(stream));
+    *ptr = static_cast<float*>(p);
+    return rc;
+}
+
+int jz_free(float* ptr, jz_stream_t stream) { return pool().release(ptr, as_stream(stream)); }
+
+int jz_pool_trim(void) {
+    JZ_INIT_OR_RETURN();
+    std::lock_guard<std::mutex> lk(pool().mu);
+    cudaDeviceSynchronize();
+    return pool().trim_locked();
+}
+
+int jz_pool_stats(size_t* live_bytes, size_t* cached_bytes, size_t* n_device_allocs, size_t* n_hits) {
+    Pool& p = pool();
+    std::lock_guard<std::mutex> lk(p.mu);
+    if (live_bytes) *live_bytes = p.live_bytes;
+    if (cached_bytes) *cached_bytes = p.cached_bytes;
+    if (n_device_allocs) *n_device_allocs = p.n_device_allocs;
+    if (n_hits) *n_hits = p.n_hits;
+    return JZ_OK;
+}
+
+int jz_memcpy_h2d(float* dst, const float* src, size_t count, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    if (count == 0) return JZ_OK;
+    if (!dst || !src) return fail(JZ_ERR_ARG, "jz_memcpy_h2d: null pointer");
+    JZ_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyHostToDevice, as_stream(stream)));
+    return JZ_OK;
+}
+
+int jz_memcpy_d2h(float* dst, const float* src, size_t count, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    if (count == 0) return JZ_OK;
+    if (!dst || !src) return fail(JZ_ERR_ARG, "jz_memcpy_d2h: null pointer");
+    JZ_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyDeviceToHost, as_stream(stream)));
+    JZ_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return JZ_OK;
+}
+
+int jz_memcpy_d2d(float* dst, const float* src, size_t count, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    if (count == 0) return JZ_OK;
+    if (!dst || !src) return fail(JZ_ERR_ARG, "jz_memcpy_d2d: null pointer");
+    JZ_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return JZ_OK;
+}
+
+}  // extern "C"
