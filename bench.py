@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Matrix<CUDAfloat> hot path (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is ONE pass of the elementwise + row/col-reduction sweep (SWEEP below: the ops of
+SURVEY.md section 8a) over one batch of synthetic fp32 input of 2^28 elements
+(16384 x 16384, 1 GiB per operand -- larger than the 126 MB L2, so no flush is needed between
+iterations).  `value` is the algorithmic HBM bytes the step moves (SURVEY 8d per-op figures)
+divided by the device time of the step, in GB/s, summed over all ranks (weak scaling: every
+GPU runs the same per-GPU batch, the path shards by independent elements, no collective).
+`e2e` is the same step driven through the C-ABI with HOST buffers: the inputs are copied from
+pinned host memory and the reduction results are read back inside the timed region.
+`gemm` carries the TFLOP/s half of the metric (fp32 GEMM, 3xTF32 and TF32 modes).
+
+--impl reference times the reference's own CPU implementation of the same step
+(oracle/_ref/libjzref.so = the unmodified Matrix<float> + OpenBLAS build; falls back to the
+pinned C restatement when that file did not travel) on a bounded sample of the batch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG2N_DEFAULT = 28
+FIFTH = 0.20000000298023224  # (float)(1.0/5.0): operator/ multiplies by the rounded reciprocal
+
+# (name, algorithmic bytes per element) -- SURVEY.md 8d
+SWEEP = [
+    ("fill", 4), ("exp", 8), ("log", 8), ("tanh", 8), ("d_tanh", 8), ("square", 8), ("affine_inplace", 8),
+    ("eleminv", 8), ("axpby", 12), ("hadamard", 12), ("chain_softplus5", 8), ("sum_dim0", 4), ("sum_dim1", 4),
+    ("max_dim0", 4), ("softmax_cols", 8), ("transpose", 8),
+]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        busy = sm[len(sm) // 2:] if sm else []          # upper half = samples under load
+        med = busy[len(busy) // 2] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- our arm
+class Sweep:
+    """the step, expressed on the C-ABI (raw pointers; no torch types cross the boundary)"""
+
+    def __init__(self, jz, rows, cols, stream):
+        import ctypes
+        self.jz, self.L, self.ct = jz, jz.lib(), ctypes
+        self.rows, self.cols, self.n, self.s = rows, cols, rows * cols, stream
+        CM = jz.CM
+        self.X = CM.randn(rows, cols, seed=0)                       # randn input (exp/tanh/affine/...)
+        self.P = CM.rand(rows, cols, seed=1)                        # rand + 0.5 for log / eleminv
+        self.L.jz_affine(self.P.ptr, self.P.ptr, self.n, 1.0, 0.5, stream)
+        self.Y = CM.randn(rows, cols, seed=2)
+        self.T = CM.empty("T", rows, cols)
+        self.v0 = CM.empty("v0", cols, 1)
+        self.v1 = CM.empty("v1", rows, 1)
+        steps = [("exp",), ("affine", 1.0, 1.0), ("log",), ("affine", FIFTH, 0.0)]
+        self.chain, self.nchain = jz._lib.make_steps(steps)
+        U = jz._lib.UNARY
+        L, X, P, Y, T, n, s, r, c = self.L, self.X.ptr, self.P.ptr, self.Y.ptr, self.T.ptr, self.n, stream, rows, cols
+        self.ops = {
+            "fill": lambda: L.jz_fill(T, n, 1.0, s),
+            "exp": lambda: L.jz_unary(U["exp"], T, X, n, s),
+            "log": lambda: L.jz_unary(U["log"], T, P, n, s),
+            "tanh": lambda: L.jz_unary(U["tanh"], T, X, n, s),
+            "d_tanh": lambda: L.jz_unary(U["dtanh"], T, X, n, s),
+            "square": lambda: L.jz_unary(U["square"], T, X, n, s),
+            "affine_inplace": lambda: L.jz_affine(T, T, n, 2.0, 1.0, s),
+            "eleminv": lambda: L.jz_eleminv(T, P, n, 1.0, s),
+            "axpby": lambda: L.jz_axpby(T, X, Y, n, 1.0, -1.0, s),
+            "hadamard": lambda: L.jz_hadamard(T, X, Y, n, s),
+            "chain_softplus5": lambda: L.jz_chain(T, X, n, self.chain, self.nchain, s),
+            "sum_dim0": lambda: L.jz_sum(self.v0.ptr, X, r, c, r, 0, s),
+            "sum_dim1": lambda: L.jz_sum(self.v1.ptr, X, r, c, r, 1, s),
+            "max_dim0": lambda: L.jz_max(self.v0.ptr, X, r, c, r, 0, s),
+            "softmax_cols": lambda: L.jz_softmax_cols(T, X, r, c, r, s),
+            "transpose": lambda: L.jz_copy2d(T, c, X, r, c, r, 1, s),
+        }
+        self.bytes_per_step = sum(b for _, b in SWEEP) * self.n
+
+    def step(self):
+        for name, _ in SWEEP:
+            rc = self.ops[name]()
+            if rc != 0:
+                raise RuntimeError(f"{name}: {self.L.jz_last_error().decode()}")
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import juzhen_b200 as jz
+
+    L = jz.lib()
+    jz._lib.check(L.jz_init(local))
+    stream = torch.cuda.current_stream().cuda_stream
+    jz.set_stream(stream)
+    rows = cols = 1 << (args.log2n // 2)
+    if args.log2n % 2:
+        cols *= 2
+    sw = Sweep(jz, rows, cols, stream)
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.jz_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = L.jz_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, launches
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_step, launches = timed(sw.step, args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    value = sw.bytes_per_step * world / (ms_step * 1e-3) / 1e9
+
+    # ---- per-op device times (CUDA events on the launching stream), for the roofline block
+    per_op = {}
+    for name, bpe in SWEEP:
+        fn = sw.ops[name]
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, args.steps)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = bpe * sw.n / (ms * 1e-3) / 1e9
+        per_op[name] = {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac": round(gbs / pk["hbm_gbs"], 3)}
+    dom = max(per_op, key=lambda k: per_op[k]["ms"] if k in ("exp", "log", "tanh", "d_tanh", "chain_softplus5") else 0)
+    roofline = {"bound": "hbm", "kernel": f"map1_v4/chain_v4 [{dom}]", "achieved": per_op[dom]["GB/s"],
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": per_op[dom]["frac"], "traffic": None,
+                "peak_source": pk["source"], "bytes_per_launch": 8 * sw.n}
+
+    # ---- e2e: same step through the C-ABI with host buffers (pinned), H2D + D2H inside the timed region
+    hx = torch.empty(sw.n, dtype=torch.float32, pin_memory=True).normal_()
+    hy = torch.empty(sw.n, dtype=torch.float32, pin_memory=True).normal_()
+    h0 = torch.empty(cols, dtype=torch.float32, pin_memory=True)
+    h1 = torch.empty(rows, dtype=torch.float32, pin_memory=True)
+
+    def e2e_step():
+        L.jz_memcpy_h2d(sw.X.ptr, hx.data_ptr(), sw.n, stream)
+        L.jz_memcpy_h2d(sw.Y.ptr, hy.data_ptr(), sw.n, stream)
+        sw.step()
+        L.jz_memcpy_d2h(h0.data_ptr(), sw.v0.ptr, cols, stream)
+        L.jz_memcpy_d2h(h1.data_ptr(), sw.v1.ptr, rows, stream)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e, _ = timed(e2e_step, e2e_steps, 1)
+    e2e = {"value": round(sw.bytes_per_step * world / (ms_e2e * 1e-3) / 1e9, 2), "unit": "GB/s",
+           "h2d_bytes_per_step": 2 * 4 * sw.n, "d2h_bytes_per_step": 4 * (rows + cols), "ms_per_step": round(ms_e2e, 3)}
+
+    # ---- GEMM half of the metric
+    gemm = {}
+    if not args.no_gemm:
+        for gn in args.gemm_n:
+            a, b = jz.CM.randn(gn, gn, seed=11), jz.CM.randn(gn, gn, seed=12)
+            c = jz.CM.empty("c", gn, gn)
+            for mode_name, mode in (("3xtf32", 0), ("tf32", 1)):
+                def g():
+                    rc = L.jz_gemm(0, 0, gn, gn, gn, 1.0, a.ptr, gn, b.ptr, gn, 0.0, c.ptr, gn, mode, stream)
+                    if rc:
+                        raise RuntimeError(L.jz_last_error().decode())
+                try:
+                    ms, _ = timed(g, max(3, args.steps // 2), 2)
+                except RuntimeError as e:
+                    gemm[f"{mode_name}_{gn}"] = {"error": str(e)}
+                    continue
+                tf = 2.0 * gn ** 3 / (ms * 1e-3) / 1e12 * world
+                peak = pk["bf16_tflops"] / 2 / (3 if mode == 0 else 1)   # TF32 = bf16/2; 3xTF32 = TF32/3
+                gemm[f"{mode_name}_{gn}"] = {"TFLOP/s": round(tf, 1), "ms": round(ms, 3), "roofline_peak": round(peak * world, 1),
+                                             "frac": round(tf / (peak * world), 3), "path": L.jz_gemm_last_path()}
+            del a, b, c
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cpu = cpu_reference_subprocess(log2n=args.cpu_log2n, steps=1)
+
+    if rank == 0:
+        line = {
+            "metric": "Elementwise/reduce HBM GB/s (sweep) and GEMM TFLOP/s, % of roofline", "value": round(value, 1),
+            "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1]: elementwise + row/col-sum sweep, 2^{args.log2n} fp32 elements "
+                                   f"({rows}x{cols}) per GPU, {len(SWEEP)} ops/step",
+                       "l2": "inputs (1 GiB/operand) larger than L2, no flush", "ops": [n for n, _ in SWEEP],
+                       "algorithmic_bytes_per_step": sw.bytes_per_step, "parallelism": f"independent shards x{world}"},
+            "frac_of_hbm_peak": round(value / world / pk["hbm_gbs"], 3),
+            "roofline": roofline, "ops": per_op, "gemm": gemm, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_step_factory(log2n):
+    """the same step on the reference's CPU implementation (bounded sample of the batch)"""
+    import numpy as np
+    import oracle
+    if oracle.ref_available():
+        O, kind = oracle.ref(), "reference"
+    else:
+        O, kind = oracle.port(), "port"
+    n = 1 << log2n
+    rows = cols = 1 << (log2n // 2)
+    if log2n % 2:
+        cols *= 2
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal(n, dtype=np.float32)
+    P = rng.random(n, dtype=np.float32) + np.float32(0.5)
+    Y = rng.standard_normal(n, dtype=np.float32)
+    X2 = np.asfortranarray(X.reshape(rows, cols, order="F"))
+    Y2 = np.asfortranarray(Y.reshape(rows, cols, order="F"))
+    ops = {
+        "fill": lambda: O.affine(X, 0.0, 1.0),
+        "exp": lambda: O.unary("exp", X), "log": lambda: O.unary("log", P), "tanh": lambda: O.unary("tanh", X),
+        "d_tanh": lambda: O.unary("dtanh", X), "square": lambda: O.unary("square", X),
+        "affine_inplace": lambda: O.affine(X, 2.0, 1.0), "eleminv": lambda: O.eleminv(P, 1.0),
+        "axpby": lambda: O.axpby(X2, 0, Y2, 0, 1.0, -1.0), "hadamard": lambda: O.hadmd(X2, 0, Y2, 0),
+        "chain_softplus5": lambda: O.chain_softplus5(X), "sum_dim0": lambda: O.sum(X2, 0, 0),
+        "sum_dim1": lambda: O.sum(X2, 0, 1), "max_dim0": lambda: O.reduce("max", X2, 0, 0),
+        "softmax_cols": lambda: O.softmax_cols(X2), "transpose": lambda: O.materialize(X2, 1),
+    }
+    threads = O.blas_threads(0) if kind == "reference" else 1
+
+    def step():
+        for name, _ in SWEEP:
+            ops[name]()
+
+    return step, n, kind, threads
+
+
+def run_cpu(log2n, steps, warmup):
+    step, n, kind, threads = cpu_step_factory(log2n)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    bytes_per_step = sum(b for _, b in SWEEP) * n
+    return {"value": round(bytes_per_step / dt / 1e9, 4), "unit": "GB/s", "cores": int(threads), "kind": kind,
+            "sample": f"one pass of the same {len(SWEEP)}-op sweep on 2^{log2n} elements "
+                      f"({dt:.2f} s/step; elementwise loops are single-threaded in the reference, "
+                      f"sum() uses OpenBLAS sgemv on {threads} threads)", "ms_per_step": round(dt * 1e3, 1)}
+
+
+def cpu_reference_subprocess(log2n, steps, warmup=0):
+    """run in a child so the reference's exit-time profiler printouts cannot pollute our JSON line"""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--_cpu_child", "--cpu-log2n", str(log2n),
+                        "--steps", str(steps), "--warmup", str(warmup)], capture_output=True, text=True, timeout=900)
+    for ln in r.stdout.splitlines():
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return {"error": (r.stderr or r.stdout)[-400:]}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_subprocess(args.cpu_log2n, max(1, args.steps), min(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rows = cols = 1 << (args.log2n // 2)
+    if "error" in res:
+        print(json.dumps({"impl": "reference", "unavailable": res["error"][:200]}))
+        return
+    line = {
+        "impl": "reference", "metric": "Elementwise/reduce HBM GB/s (sweep) and GEMM TFLOP/s, % of roofline",
+        "value": res["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1]: elementwise + row/col-sum sweep, 2^{args.log2n} fp32 elements "
+                               f"({rows}x{cols}) per GPU, {len(SWEEP)} ops/step",
+                   "ops": [n for n, _ in SWEEP], "note": "reference CPU path timed on a bounded sample (see cpu_baseline.sample)"},
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=LOG2N_DEFAULT)
+    ap.add_argument("--cpu-log2n", type=int, default=24, dest="cpu_log2n")
+    ap.add_argument("--gemm-n", type=int, nargs="*", default=[4096, 8192], dest="gemm_n")
+    ap.add_argument("--no-gemm", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--_cpu_child", action="store_true")
+    args = ap.parse_args()
+    if args._cpu_child:
+        print(json.dumps(run_cpu(args.cpu_log2n, args.steps, args.warmup)))
+        return
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,124 @@
+"""GPU parity tests for the GEMM behind operator* (SURVEY 8a row a17), through the C-ABI.
+
+Tolerances (north_star): relative Frobenius error <= 1e-5 in 3xTF32 mode (the default) and
+<= 1e-3 in TF32 mode, against the reference's CPU result (OpenBLAS fixture) and against the
+oracle's double-accumulated product.  All four op(A), op(B) combinations, ragged tiles,
+odd leading dimensions (the n = 1001 case of tests/testEigen.cu), alpha/beta, fused epilogue.
+"""
+import numpy as np
+import pytest
+
+from conftest import bits, rel_fro
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"3xtf32": 1e-5, "tf32": 1e-3, "fp32": 1e-5, "bf16": 1e-3}
+
+
+def F(a):
+    return np.asfortranarray(a, dtype=np.float32)
+
+
+def operands(jz, P, Q, ta, tb):
+    a = jz.CM(F(P.T)).T() if ta else jz.CM(P)
+    b = jz.CM(F(Q.T)).T() if tb else jz.CM(Q)
+    return a, b
+
+
+@pytest.mark.parametrize("name", ["g1", "g2", "g3", "g4"])
+def test_gemm_vs_reference_fixture(jz, golden, name):
+    P, Q = golden[f"gemm_{name}_A"], golden[f"gemm_{name}_B"]
+    for ta in (0, 1):
+        for tb in (0, 1):
+            a, b = operands(jz, P, Q, ta, tb)
+            got = (a * b).to_host()
+            assert rel_fro(got, golden[f"gemm_{name}_blas_{ta}{tb}"]) < 1e-5, (name, ta, tb)
+
+
+def test_gemm_odd_leading_dimension(jz, golden):
+    P, Q = golden["gemm_odd_A"], golden["gemm_odd_B"]
+    got = (jz.CM(P) * jz.CM(Q).T()).to_host()
+    assert rel_fro(got, golden["gemm_odd_blas_01"]) < 1e-5
+
+
+def test_gemm_shape_error(jz):
+    with pytest.raises(ValueError):
+        jz.CM.ones_(3, 4) * jz.CM.ones_(3, 4)
+
+
+@pytest.mark.parametrize("mode", ["3xtf32", "tf32", "fp32"])
+@pytest.mark.parametrize("shape", [(256, 256, 256), (384, 300, 520), (130, 1000, 70), (1024, 512, 768), (515, 2049, 257)])
+def test_gemm_all_flags_vs_oracle(jz, port, mode, shape):
+    m, k, n = shape
+    rng = np.random.default_rng(m * 7 + k * 3 + n)
+    P, Q = F(rng.standard_normal((m, k))), F(rng.standard_normal((k, n)))
+    truth = port.gemm(P, 0, Q, 0, f64=True)
+    for ta in (0, 1):
+        for tb in (0, 1):
+            a, b = operands(jz, P, Q, ta, tb)
+            got = a.dot(b, mode=jz._lib.GEMM_MODES[mode]).to_host()
+            err = rel_fro(got, truth)
+            path = jz.lib().jz_gemm_last_path()
+            print(f"gemm {mode} {shape} ta={ta} tb={tb}: rel_fro={err:.3e} path={path}")
+            assert err < TOL[mode], (mode, shape, ta, tb, err)
+            if mode != "fp32" and min(m, n) >= 64 and m * n * k >= (1 << 22):
+                assert path == 1, "expected the tcgen05 kernel"
+
+
+def test_gemm_tf32_is_actually_tf32_and_3x_is_fp32_grade(jz, port):
+    """the two modes must differ the way the README says (~1e-3 vs fp32-grade)"""
+    rng = np.random.default_rng(3)
+    P, Q = F(rng.standard_normal((512, 512))), F(rng.standard_normal((512, 512)))
+    truth = port.gemm(P, 0, Q, 0, f64=True)
+    a, b = jz.CM(P), jz.CM(Q)
+    e3 = rel_fro(a.dot(b, mode=0).to_host(), truth)
+    e1 = rel_fro(a.dot(b, mode=1).to_host(), truth)
+    ef = rel_fro(a.dot(b, mode=2).to_host(), truth)
+    print(f"rel_fro: 3xtf32={e3:.3e} tf32={e1:.3e} fp32-simt={ef:.3e}")
+    assert e3 < 2e-6 and 1e-5 < e1 < 1e-3 and ef < 1e-6
+
+
+def test_gemm_alpha_beta(jz, port):
+    rng = np.random.default_rng(9)
+    m, k, n = 300, 260, 280
+    P, Q, C0 = F(rng.standard_normal((m, k))), F(rng.standard_normal((k, n))), F(rng.standard_normal((m, n)))
+    truth = 0.75 * port.gemm(P, 0, Q, 0, f64=True).astype(np.float64) - 0.5 * C0
+    L = jz.lib()
+    for mode in (0, 2):
+        a, b, c = jz.CM(P), jz.CM(Q), jz.CM(C0)
+        jz._lib.check(L.jz_gemm(0, 0, m, n, k, 0.75, a.ptr, m, b.ptr, k, -0.5, c.ptr, m, mode, None))
+        assert rel_fro(c.to_host(), truth) < 1e-5
+
+
+def test_gemm_fused_epilogue_equals_separate_kernels(jz, golden):
+    """config 1: log(exp(A*B/n)+1)/5 as a GEMM epilogue == GEMM then the elementwise chain,
+    and both match the reference's CPU result."""
+    A, B = golden["c1_A"], golden["c1_B"]
+    n = A.shape[0]
+    a, b = jz.CM(A), jz.CM(B)
+    sep = jz.log(jz.exp((a * b) / float(n)) + 1.0) / 5.0
+    steps = [("affine", float(np.float32(1.0 / n)), 0.0), ("exp",), ("affine", 1.0, 1.0), ("log",),
+             ("affine", float(np.float32(1.0 / 5.0)), 0.0)]
+    arr, ns = jz._lib.make_steps(steps)
+    fused = jz.CM.empty("f", n, n)
+    jz._lib.check(jz.lib().jz_gemm_chain(0, 0, n, n, n, 1.0, a.ptr, n, b.ptr, n, fused.ptr, n, arr, ns, -1, None))
+    assert np.array_equal(bits(sep.to_host()), bits(fused.to_host()))
+    assert rel_fro(fused.to_host(), golden["c1_out"]) < 1e-5
+
+
+def test_gemm_4096_sampled_block_vs_oracle(jz, port):
+    """benchmark-size product: a 4096 x 64 column block recomputed by the oracle in double"""
+    n = 4096
+    a, b = jz.CM.randn(n, n, seed=1), jz.CM.randn(n, n, seed=2)
+    for mode, tol in ((0, 1e-5), (1, 1e-3)):
+        c = a.dot(b, mode=mode)
+        assert jz.lib().jz_gemm_last_path() == 1
+        A = a.to_host()
+        Bc = b.columns(1000, 1064).to_host()
+        truth = port.gemm(A, 0, Bc, 0, f64=True)
+        assert rel_fro(c.columns(1000, 1064).to_host(), truth) < tol
+        # A^T path on the same data: (A^T)^T B == A B
+        at = jz.CM.empty("at", n, n)
+        jz._lib.check(jz.lib().jz_copy2d(at.ptr, n, a.ptr, n, n, n, 1, None))
+        c2 = at.T().dot(b, mode=mode)
+        assert rel_fro(c2.columns(1000, 1064).to_host(), truth) < tol
