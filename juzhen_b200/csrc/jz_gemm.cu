@@ -142,7 +142,8 @@ constexpr int UMMA_K = 8;            // tf32: 32 bytes per MMA k-step
 constexpr int TILE_M = 128;          // rows of A per CTA (TMEM lanes)
 constexpr int TILE_N = 256;          // accumulator columns
 constexpr int A_BYTES = TILE_M * BK * 4;  // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // TMA warp + MMA warp + 8 epilogue warps
 
 template <int CG> __host__ __device__ constexpr int b_rows() { return CG == 2 ? 128 : 256; }
 template <int CG> __host__ __device__ constexpr int b_bytes() { return b_rows<CG>() * BK * 4; }
@@ -284,10 +285,21 @@ struct GemmArgs {
     float* C;
     size_t ldc;
     unsigned tiles_m, tiles_n;  // in units of (CG*128) x 256 tiles
+    int kb_per_chunk;           // k-blocks accumulated inside TMEM before promotion to registers
     ChainParams chain;
 };
 
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // One (CG*128) x 256 output tile per CTA group.  tmA*/tmB*: [rows][K] K-major tensor maps.
+//
+// Accumulation is two-level: the tensor core adds each MMA's partial product into the TMEM
+// accumulator with truncation (measured: relative error 6.9e-9 * k, i.e. biased, linear in the
+// length of the chain), so only `kb_per_chunk` k-blocks are chained inside TMEM; the epilogue
+// warps then promote the chunk into fp32 REGISTER accumulators with round-to-nearest adds while
+// the MMA warp is already filling the other TMEM buffer (2 x 256 columns = all 512).
 template <int CG, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -301,13 +313,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-    // barriers: full[STAGES], empty[STAGES], tmem_full, then the TMEM base slot
+    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+    auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+    auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
     uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -326,6 +340,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const int n0 = int(tn) * TILE_N;
     const int nb0 = n0 + (CG == 2 ? int(rank) * 128 : 0);         // first B row (= C column) this CTA loads
     const int num_kb = int((args.k + BK - 1) / BK);
+    const int kbc = args.kb_per_chunk;
+    const int num_chunks = (num_kb + kbc - 1) / kbc;
 
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
@@ -341,11 +357,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 mbar_init(full_bar(s), 1);
                 mbar_init(empty_bar(s), 1);
             }
-            mbar_init(tmem_full_bar, 1);
+            for (int b = 0; b < 2; b++) {
+                mbar_init(tmem_full_bar(b), 1);
+                mbar_init(tmem_empty_bar(b), NUM_EPI_WARPS * CG);  // every epilogue warp of the pair
+            }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<CG>(tmem_slot, TILE_N);
+        tmem_alloc<CG>(tmem_slot, 2 * TILE_N);
     }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -374,65 +393,94 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader) {
             uint32_t stage = 0, phase = 0;
+            int chunk = 0, in_chunk = 0;
             for (int kb = 0; kb < num_kb; kb++) {
+                const uint32_t buf = uint32_t(chunk) & 1u;
+                if (in_chunk == 0) {  // this TMEM buffer must have been drained by every epilogue warp
+                    mbar_wait(tmem_empty_bar(buf), ((uint32_t(chunk) >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                }
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
+                const bool chunk_end = (in_chunk == kbc - 1) || (kb == num_kb - 1);
                 if (elect_one()) {
+                    const uint32_t d = tmem_base + buf * TILE_N;
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     const uint32_t a_hi = sa, b_hi = sa + A_BYTES;
                     const uint32_t a_lo = sa + A_BYTES + B_BYTES, b_lo = sa + 2 * A_BYTES + B_BYTES;
-                    uint32_t first = kb == 0 ? 0u : 1u;
+                    uint32_t acc = in_chunk == 0 ? 0u : 1u;
                     if (SPLIT) {
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ks++) {
-                            umma_tf32<CG>(tmem_base, make_smem_desc(a_lo + ks * 32), make_smem_desc(b_hi + ks * 32), IDESC, first);
-                            first = 1u;
+                            umma_tf32<CG>(d, make_smem_desc(a_lo + ks * 32), make_smem_desc(b_hi + ks * 32), IDESC, acc);
+                            acc = 1u;
                         }
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ks++)
-                            umma_tf32<CG>(tmem_base, make_smem_desc(a_hi + ks * 32), make_smem_desc(b_lo + ks * 32), IDESC, 1u);
+                            umma_tf32<CG>(d, make_smem_desc(a_hi + ks * 32), make_smem_desc(b_lo + ks * 32), IDESC, 1u);
                     }
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ks++) {
-                        umma_tf32<CG>(tmem_base, make_smem_desc(a_hi + ks * 32), make_smem_desc(b_hi + ks * 32), IDESC, first);
-                        first = 1u;
+                        umma_tf32<CG>(d, make_smem_desc(a_hi + ks * 32), make_smem_desc(b_hi + ks * 32), IDESC, acc);
+                        acc = 1u;
                     }
-                    umma_commit<CG>(empty_bar(stage));                       // frees this smem stage (both CTAs)
-                    if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar);    // accumulator complete
+                    umma_commit<CG>(empty_bar(stage));                   // frees this smem stage (both CTAs)
+                    if (chunk_end) umma_commit<CG>(tmem_full_bar(buf));  // chunk accumulator complete
                 }
                 __syncwarp();
+                if (chunk_end) { chunk++; in_chunk = 0; } else { in_chunk++; }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> registers -> global (column-major) =====================
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        // ===================== epilogue: TMEM chunks -> fp32 registers (RN) -> global =====================
+        const int e = warp - 2;
+        const int quarter = warp & 3;   // TMEM lane quarter this warp may access (hardware: warp id % 4)
+        const int half = e >> 2;        // which 128 of the 256 accumulator columns
         const int lane = threadIdx.x & 31;
+        float acc[128];
+#pragma unroll
+        for (int i = 0; i < 128; i++) acc[i] = 0.0f;
+        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * 128);
+        const uint32_t empty0 = tmem_empty_bar(0) & 0xFEFFFFFFu, empty1 = tmem_empty_bar(1) & 0xFEFFFFFFu;
+        for (int chunk = 0; chunk < num_chunks; chunk++) {
+            const uint32_t buf = uint32_t(chunk) & 1u;
+            mbar_wait(tmem_full_bar(buf), (uint32_t(chunk) >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(lane_addr + buf * TILE_N + p * 32, r);
+#pragma unroll
+                for (int c = 0; c < 32; c++) acc[p * 32 + c] = __fadd_rn(acc[p * 32 + c], __uint_as_float(r[c]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(buf ? empty1 : empty0);  // on the leader CTA's barrier
+        }
         const size_t row = size_t(m0) + quarter * 32 + lane;
         const bool row_ok = row < args.m;
         float* crow = args.C + row;
-#pragma unroll 1
-        for (int c0 = 0; c0 < TILE_N; c0 += 32) {
-            if (size_t(n0 + c0) >= args.n) break;  // warp-uniform
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), r);
-            float v[32];
+        const size_t ncol0 = size_t(n0) + half * 128;
 #pragma unroll
-            for (int c = 0; c < 32; c++) v[c] = args.alpha * __uint_as_float(r[c]);
-            if (args.beta != 0.0f) {
+        for (int p = 0; p < 4; p++) {
+            if (ncol0 + p * 32 < args.n) {  // warp-uniform
+                float v[32];
+#pragma unroll
+                for (int c = 0; c < 32; c++) v[c] = args.alpha * acc[p * 32 + c];
+                if (args.beta != 0.0f) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const size_t col = ncol0 + p * 32 + c;
+                        if (row_ok && col < args.n) v[c] += args.beta * crow[col * args.ldc];
+                    }
+                }
+                if (args.chain.n) apply_chain<32>(v, args.chain);
 #pragma unroll
                 for (int c = 0; c < 32; c++) {
-                    const size_t col = size_t(n0 + c0 + c);
-                    if (row_ok && col < args.n) v[c] += args.beta * crow[col * args.ldc];
+                    const size_t col = ncol0 + p * 32 + c;
+                    if (row_ok && col < args.n) crow[col * args.ldc] = v[c];  // a warp writes 32 consecutive floats
                 }
-            }
-            if (args.chain.n) apply_chain<32>(v, args.chain);
-#pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const size_t col = size_t(n0 + c0 + c);
-                if (row_ok && col < args.n) crow[col * args.ldc] = v[c];  // a warp writes 32 consecutive floats
             }
         }
     }
@@ -440,7 +488,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
-    if (warp == 1) tmem_dealloc<CG>(tmem_base, TILE_N);
+    if (warp == 1) tmem_dealloc<CG>(tmem_base, 2 * TILE_N);
 }
 
 // ----------------------------------------------------------------------- operand pre-pass
@@ -552,6 +600,18 @@ static int pick_cg() {
     return g_cg;
 }
 
+// k-blocks (of 32) chained inside TMEM before RN promotion: 3xTF32 keeps the chain short for
+// fp32-grade accuracy; TF32 mode is input-rounding dominated so long chains are harmless.
+static int chunk_kb(bool split) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = std::getenv("JZ_GEMM_CHUNK_KB");
+        forced = e ? std::atoi(e) : 0;
+    }
+    if (forced > 0) return forced;
+    return split ? 4 : 32;
+}
+
 struct Operand {
     const float* hi = nullptr;
     const float* lo = nullptr;
@@ -652,6 +712,7 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         args.alpha = alpha; args.beta = beta;
         args.C = C; args.ldc = ldc;
         args.tiles_m = args.tiles_n = 0;
+        args.kb_per_chunk = chunk_kb(split);
         args.chain = chain;
         const int cg = pick_cg();
         if (cg == 2) rc = split ? launch_tc<2, true>(a, b, args, s) : launch_tc<2, false>(a, b, args, s);

@@ -173,6 +173,50 @@ __global__ void __launch_bounds__(kTile* kTileRows) transpose_kernel(float* dst,
     }
 }
 
+// 64 x 64 tiles, 128-bit global accesses on BOTH sides (requires 16-byte aligned pointers and
+// ld % 4 == 0; interior tiles only -- ragged edges take the scalar path inside the same kernel).
+// Shared-memory pitch 65 keeps the transposed reads at most 2-way conflicted.
+__global__ void __launch_bounds__(256) transpose64_kernel(float* dst, size_t ldd, const float* src, size_t lds,
+                                                          size_t rows, size_t cols, size_t tiles_i, size_t tiles_j) {
+    __shared__ float tile[64][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const size_t ntiles = tiles_i * tiles_j;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t ti = t % tiles_i, tj = t / tiles_i;
+        const size_t i0 = ti * 64, j0 = tj * 64;
+        const bool full = i0 + 64 <= rows && j0 + 64 <= cols;
+        if (full) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int il = ty + 16 * r;  // row of dst == column of src
+                const float4 v = *reinterpret_cast<const float4*>(src + (i0 + il) * lds + j0 + 4 * tx);
+                tile[il][4 * tx + 0] = v.x; tile[il][4 * tx + 1] = v.y;
+                tile[il][4 * tx + 2] = v.z; tile[il][4 * tx + 3] = v.w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int jl = ty + 16 * r;
+                float4 v;
+                v.x = tile[4 * tx + 0][jl]; v.y = tile[4 * tx + 1][jl];
+                v.z = tile[4 * tx + 2][jl]; v.w = tile[4 * tx + 3][jl];
+                *reinterpret_cast<float4*>(dst + (j0 + jl) * ldd + i0 + 4 * tx) = v;
+            }
+        } else {
+            for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+                const int il = e >> 6, jl = e & 63;
+                if (i0 + il < rows && j0 + jl < cols) tile[il][jl] = src[(i0 + il) * lds + j0 + jl];
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+                const int jl = e >> 6, il = e & 63;
+                if (i0 + il < rows && j0 + jl < cols) dst[(j0 + jl) * ldd + i0 + il] = tile[il][jl];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // out(i,j) = f(opA(i,j), opB(i,j)) with at least one transposed operand
 template <bool TA, bool TB, class F>
 __global__ void __launch_bounds__(kTile* kTileRows) bin2d_t_kernel(float* out, size_t ldo, size_t rows, size_t cols,
@@ -250,6 +294,11 @@ int jz_copy2d(float* dst, size_t ldd, const float* src, size_t lds, size_t rows,
         if (ldd == rows && lds == rows) return jz_copy(dst, src, rows * cols, stream);
         const bool vec = aligned16(dst) && aligned16(src) && ldd % 4 == 0 && lds % 4 == 0;
         return launch_map2d(Copy2dOp{dst, ldd, src, lds}, rows, cols, vec, s);
+    }
+    if (aligned16(dst) && aligned16(src) && ldd % 4 == 0 && lds % 4 == 0 && rows >= 64 && cols >= 64) {
+        const size_t t64_i = ceil_div(rows, size_t(64)), t64_j = ceil_div(cols, size_t(64));
+        JZ_LAUNCH(transpose64_kernel, tile_grid(t64_i * t64_j), 256, 0, s, dst, ldd, src, lds, rows, cols, t64_i, t64_j);
+        return JZ_OK;
     }
     const size_t tiles_i = ceil_div(rows, kTile), tiles_j = ceil_div(cols, kTile);
     JZ_LAUNCH(transpose_kernel, tile_grid(tiles_i * tiles_j), dim3(kTile, kTileRows), 0, s, dst, ldd, src, lds, rows,

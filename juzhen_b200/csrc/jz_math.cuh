@@ -29,6 +29,11 @@ __device__ __forceinline__ float eleminv_rn(float x, float l) { return __fdiv_rn
 // residual terr (FMA), and one correction step on the rounded quotient.
 __device__ __forceinline__ float dtanh_acc(float x) {
     const float ax = fabsf(x);
+    if (ax > 40.0f) {
+        // exp(-2|x|) approaches the subnormal range: its fp32 quantisation alone would cost > 2 ulp
+        // of the result.  This branch is never taken for activations in practice; do it in double.
+        return float(4.0 * exp(-2.0 * double(ax)));   // (1+e)^2 == 1 to 1e-34 here
+    }
     const float e = expf(-2.0f * ax);
     const float s = __fadd_rn(1.0f, e);
     const float serr = __fsub_rn(e, __fsub_rn(s, 1.0f));

@@ -283,6 +283,83 @@ __global__ void __launch_bounds__(256) softmax_warp_kernel(float* out, const flo
     }
 }
 
+// ---- register-cached column softmax: the column is read ONCE (128-bit loads), kept in registers
+// through max / exp / sum / scale, and written ONCE: 8 B/elem of HBM traffic, the algorithmic
+// minimum.  G threads cooperate on one column: a warp (G = 32, 8 columns per CTA) for rows up to
+// 2048, a whole 512-thread CTA (G = 512) for rows up to 32768.  mode 1 fuses the softmax-CE
+// gradient -(y - s)/nb (ml/layer.hpp:263) into the same pass.
+template <int NV, bool BLOCK>
+__global__ void __launch_bounds__(BLOCK ? 512 : 256)
+softmax_reg_kernel(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode, float rnb) {
+    constexpr int G = BLOCK ? 512 : 32;
+    __shared__ float red[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = BLOCK ? threadIdx.x : lane;
+    const size_t n4 = rows >> 2;
+    const size_t col_step = BLOCK ? gridDim.x : size_t(gridDim.x) * 8;
+    for (size_t c = BLOCK ? blockIdx.x : size_t(blockIdx.x) * 8 + warp; c < cols; c += col_step) {
+        const float4* col = reinterpret_cast<const float4*>(a + c * ld);
+        float4 v[NV];
+        float m = -1e30f;
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const size_t i = size_t(g) + size_t(q) * G;
+            if (i < n4) {
+                v[q] = col[i];
+                m = fmaxf(m, fmaxf(fmaxf(v[q].x, v[q].y), fmaxf(v[q].z, v[q].w)));
+            }
+        }
+        m = warp_reduce<MaxOp>(m);
+        if (BLOCK) {
+            __syncthreads();  // protects `red` from the previous column's readers
+            if (lane == 0) red[warp] = m;
+            __syncthreads();
+            m = red[lane & 15];
+            m = warp_reduce<MaxOp>(m);
+        }
+        float z = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const size_t i = size_t(g) + size_t(q) * G;
+            if (i < n4) {
+                v[q].x = expf(__fadd_rn(-m, v[q].x)); v[q].y = expf(__fadd_rn(-m, v[q].y));
+                v[q].z = expf(__fadd_rn(-m, v[q].z)); v[q].w = expf(__fadd_rn(-m, v[q].w));
+                z += (v[q].x + v[q].y) + (v[q].z + v[q].w);
+            }
+        }
+        z = warp_reduce<SumOp>(z);
+        if (BLOCK) {
+            __syncthreads();
+            if (lane == 0) red[warp] = z;
+            __syncthreads();
+            z = red[lane & 15];
+            // 16 partials duplicated over 32 lanes: reduce over 16 lanes only
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+        }
+        const float inv = __fdiv_rn(1.0f, z);
+        float4* o4 = reinterpret_cast<float4*>(out + c * rows);
+        const float4* y4 = reinterpret_cast<const float4*>(mode == 1 ? y + c * rows : nullptr);
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const size_t i = size_t(g) + size_t(q) * G;
+            if (i < n4) {
+                float4 r;
+                r.x = __fmul_rn(v[q].x, inv); r.y = __fmul_rn(v[q].y, inv);
+                r.z = __fmul_rn(v[q].z, inv); r.w = __fmul_rn(v[q].w, inv);
+                if (mode == 1) {
+                    const float4 t = y4[i];
+                    r.x = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-r.x, t.x), 0.0f)), 0.0f);
+                    r.y = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-r.y, t.y), 0.0f)), 0.0f);
+                    r.z = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-r.z, t.z), 0.0f)), 0.0f);
+                    r.w = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-r.w, t.w), 0.0f)), 0.0f);
+                }
+                o4[i] = r;
+            }
+        }
+    }
+}
+
 struct CeGradF {
     float rnb;
     __device__ __forceinline__ float operator()(float s, float y) const {
@@ -476,6 +553,30 @@ static int softmax_impl(float* out, const float* a, const float* y, size_t rows,
         return JZ_OK;
     }
     const bool vec = aligned16(a) && ld % 4 == 0;
+    const bool regs_ok = vec && rows % 4 == 0 && aligned16(out) && (mode == 0 || aligned16(y)) && rows <= 32768;
+    if (regs_ok) {
+        const size_t n4 = rows >> 2;
+        if (n4 <= 512) {  // one warp per column
+            const size_t blocks = ceil_div(cols, size_t(8));
+            const unsigned grid = unsigned(blocks < cap ? blocks : cap);
+#define JZ_SM_WARP(NV) JZ_LAUNCH((softmax_reg_kernel<NV, false>), grid, 256, 0, s, out, a, y, rows, cols, ld, mode, rnb)
+            if (n4 <= 32) JZ_SM_WARP(1);
+            else if (n4 <= 64) JZ_SM_WARP(2);
+            else if (n4 <= 128) JZ_SM_WARP(4);
+            else if (n4 <= 256) JZ_SM_WARP(8);
+            else JZ_SM_WARP(16);
+#undef JZ_SM_WARP
+        } else {          // one 512-thread CTA per column
+            const unsigned grid = unsigned(cols < cap * 4 ? cols : cap * 4);
+#define JZ_SM_BLOCK(NV) JZ_LAUNCH((softmax_reg_kernel<NV, true>), grid, 512, 0, s, out, a, y, rows, cols, ld, mode, rnb)
+            if (n4 <= 1024) JZ_SM_BLOCK(2);
+            else if (n4 <= 2048) JZ_SM_BLOCK(4);
+            else if (n4 <= 4096) JZ_SM_BLOCK(8);
+            else JZ_SM_BLOCK(16);
+#undef JZ_SM_BLOCK
+        }
+        return JZ_OK;
+    }
     const size_t blocks = ceil_div(cols, size_t(8));
     const unsigned grid = unsigned(blocks < cap ? blocks : cap);
     if (vec) JZ_LAUNCH((softmax_warp_kernel<true>), grid, 256, 0, s, out, a, rows, cols, ld);
