@@ -174,7 +174,10 @@ __global__ void __launch_bounds__(kThreads) fill_s(float* out, size_t n, float v
 
 // fused chain: UNROLL x 4 values per thread in registers, every step applied to the
 // whole register tile so the per-step dispatch is amortised over 16 elements.
-__global__ void __launch_bounds__(kThreads) chain_v4(float* out, const float* in, size_t n, ChainParams c) {
+__global__ void __launch_bounds__(kThreads) chain_v4(float* out, const float* in, size_t n, ChainParams cp) {
+    __shared__ ChainParams c;
+    stage_chain(&c, cp, threadIdx.x);
+    __syncthreads();
     const size_t n4 = n >> 2;
     const float4* in4 = reinterpret_cast<const float4*>(in);
     float4* out4 = reinterpret_cast<float4*>(out);
@@ -203,7 +206,10 @@ __global__ void __launch_bounds__(kThreads) chain_v4(float* out, const float* in
     }
 }
 
-__global__ void __launch_bounds__(kThreads) chain_s(float* out, const float* in, size_t n, ChainParams c) {
+__global__ void __launch_bounds__(kThreads) chain_s(float* out, const float* in, size_t n, ChainParams cp) {
+    __shared__ ChainParams c;
+    stage_chain(&c, cp, threadIdx.x);
+    __syncthreads();
     for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += size_t(gridDim.x) * kThreads) {
         float t[1] = {in[i]};
         apply_chain<1>(t, c);

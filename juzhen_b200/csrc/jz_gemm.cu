@@ -37,7 +37,10 @@ constexpr int SBM = 64, SBN = 64, SBK = 16;
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_simt_kernel(size_t m, size_t n, size_t k, float alpha, const float* A,
                                                          size_t lda, const float* B, size_t ldb, float beta, float* C,
-                                                         size_t ldc, ChainParams chain) {
+                                                         size_t ldc, ChainParams chain_p) {
+    __shared__ ChainParams chain;
+    stage_chain(&chain, chain_p, threadIdx.x);
+    __syncthreads();
     __shared__ float As[SBK][SBM + 4];
     __shared__ float Bs[SBK][SBN + 4];
     const int t = threadIdx.x;
@@ -122,7 +125,10 @@ static int launch_simt(int ta, int tb, size_t m, size_t n, size_t k, float alpha
 // u == nullptr means the product term is absent (k == 0).
 __global__ void __launch_bounds__(256) rank1_kernel(size_t m, size_t n, float alpha, const float* u, size_t su,
                                                     const float* v, size_t sv, float beta, float* C, size_t ldc,
-                                                    ChainParams chain) {
+                                                    ChainParams chain_p) {
+    __shared__ ChainParams chain;
+    stage_chain(&chain, chain_p, threadIdx.x);
+    __syncthreads();
     for (size_t j = blockIdx.y; j < n; j += gridDim.y) {
         const float vj = u ? alpha * v[j * sv] : 0.0f;
         for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < m; i += size_t(gridDim.x) * 256) {
@@ -311,6 +317,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     constexpr uint32_t IDESC = make_idesc_tf32(CG * 128, TILE_N);
 
     extern __shared__ uint8_t smem_raw[];
+    __shared__ ChainParams s_chain;
+    stage_chain(&s_chain, args.chain, threadIdx.x);  // visible after the setup barrier below
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
     // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base slot
@@ -475,7 +483,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         if (row_ok && col < args.n) v[c] += args.beta * crow[col * args.ldc];
                     }
                 }
-                if (args.chain.n) apply_chain<32>(v, args.chain);
+                if (s_chain.n) apply_chain<32>(v, s_chain);
 #pragma unroll
                 for (int c = 0; c < 32; c++) {
                     const size_t col = ncol0 + p * 32 + c;

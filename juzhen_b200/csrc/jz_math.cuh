@@ -22,27 +22,50 @@ __device__ __forceinline__ float affine_rn(float x, float s1, float a) {
 // IEEE fp32 division gives the same bits.
 __device__ __forceinline__ float eleminv_rn(float x, float l) { return __fdiv_rn(l, x); }
 
+// exp(t) for t in [-88, 0] with < 1 ulp error (CUDA's expf is documented at 2 ulp, which alone would
+// use up the whole d_tanh budget).  t = n*ln2 + r with |r| <= ln2/2: n from the round-to-nearest
+// magic-number trick, r by a two-term Cody-Waite reduction (the first FMA is exact), exp(r) =
+// 1 + r + r^2*P5(r) (fit error 0.012 ulp), and the 2^n scaling is an integer add on the exponent.
+__device__ __forceinline__ float exp_neg_1ulp(float t) {
+    const float z = __fmaf_rn(t, 1.4426950408889634f, 12582912.0f);
+    const float n = __fsub_rn(z, 12582912.0f);
+    float r = __fmaf_rn(n, -0.693145751953125f, t);
+    r = __fmaf_rn(n, -1.4286068203094173e-06f, r);
+    float p = 0.00019899278413504362f;
+    p = __fmaf_rn(p, r, 0.0013933645095676184f);
+    p = __fmaf_rn(p, r, 0.0083332983776927f);
+    p = __fmaf_rn(p, r, 0.04166646674275398f);
+    p = __fmaf_rn(p, r, 0.1666666716337204f);
+    p = __fmaf_rn(p, r, 0.5f);
+    p = __fmaf_rn(p, __fmul_rn(r, r), r);
+    p = __fadd_rn(1.0f, p);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(z) << 23));
+}
+
 // d_tanh(x) = 1 - tanh(x)^2 = 4e / (1+e)^2 with e = exp(-2|x|).
 // The reference evaluates 1 - tanh^2 in double (cpp/matrix.hpp:301-324); in fp32 that form
 // cancels catastrophically for |x| >~ 5, so the quotient form is used with a compensated
 // denominator: s = fl(1+e) with exact residual serr (Fast2Sum, 1 >= e), t = fl(s*s) with exact
-// residual terr (FMA), and one correction step on the rounded quotient.
+// residual terr (FMA), an FMA-refined quotient q = 4e/t and one correction step for t's residual.
 __device__ __forceinline__ float dtanh_acc(float x) {
     const float ax = fabsf(x);
-    if (ax > 40.0f) {
-        // exp(-2|x|) approaches the subnormal range: its fp32 quantisation alone would cost > 2 ulp
-        // of the result.  This branch is never taken for activations in practice; do it in double.
+    if (!(ax <= 40.0f)) {
+        // exp(-2|x|) approaches the subnormal range (its fp32 quantisation alone would cost > 2 ulp),
+        // or x is inf / NaN.  Never taken for activations in practice; do it in double.
         return float(4.0 * exp(-2.0 * double(ax)));   // (1+e)^2 == 1 to 1e-34 here
     }
-    const float e = expf(-2.0f * ax);
+    const float e = exp_neg_1ulp(-2.0f * ax);
     const float s = __fadd_rn(1.0f, e);
     const float serr = __fsub_rn(e, __fsub_rn(s, 1.0f));
     const float t = __fmul_rn(s, s);
     const float terr = __fmaf_rn(s, s, -t);
     const float c = __fmaf_rn(2.0f * s, serr, terr);  // (1+e)^2 = t + c (+ serr^2 ~ 2^-48)
     const float num = 4.0f * e;
-    const float q0 = __fdiv_rn(num, t);
-    return __fmaf_rn(-q0, __fdividef(c, t), q0);
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(t));  // t in [1, 4]
+    const float q0 = __fmul_rn(num, rc);
+    const float q = __fmaf_rn(__fmaf_rn(-q0, t, num), rc, q0);  // residual-corrected quotient
+    return __fmaf_rn(-q, __fmul_rn(c, rc), q);
 }
 
 template <int OP>
@@ -94,9 +117,21 @@ struct ChainParams {
     float a[JZ_MAX_CHAIN];
 };
 
+// Applies the steps in order to a register tile.  `c` must live in SHARED memory (stage it with
+// stage_chain): indexing a kernel-parameter struct with the runtime step counter makes nvcc emit a
+// compare-and-select ladder over the whole constant bank (measured: 76 of 162 instructions per
+// element in the first chain kernel), whereas an LDS per step is free.
 template <int N>
 __device__ __forceinline__ void apply_chain(float (&v)[N], const ChainParams& c) {
-    for (int s = 0; s < c.n; s++) apply_step<N>(v, c.kind[s], c.s1[s], c.a[s]);
+    const int n = c.n;
+#pragma unroll 1
+    for (int s = 0; s < n; s++) apply_step<N>(v, c.kind[s], c.s1[s], c.a[s]);
+}
+
+// cooperative copy of the kernel-parameter chain into shared memory (call before __syncthreads)
+__device__ __forceinline__ void stage_chain(ChainParams* dst, const ChainParams& src, int tid) {
+    constexpr int kWords = int(sizeof(ChainParams) / sizeof(int));
+    if (tid < kWords) reinterpret_cast<int*>(dst)[tid] = reinterpret_cast<const int*>(&src)[tid];
 }
 
 inline int make_chain(ChainParams& c, const jz_step* steps, int nsteps) {

@@ -282,7 +282,9 @@ class CM:
         return self.add(-float(r), 1.0, inplace=True)
 
     def __truediv__(self, r):
-        if isinstance(r, CM):  # A / B = hadmd(A, B.eleminv(1.0))
+        if isinstance(r, CM):  # A / B = hadmd(A, B.eleminv(1.0)); shapes are checked before any launch
+            if self.num_row() != r.num_row() or self.num_col() != r.num_col():
+                raise _lib.JzShapeError("Matrix dimensions are not compatible")
             return hadmd(self, r.eleminv(1.0), inplace_rhs=True)
         return self.scale(float(np.float32(1.0 / float(r))))  # multiply by (float)(1.0/r)
 

@@ -40,11 +40,11 @@ def test_testbasic_golden_vector(jz, golden):
 
 def test_shape_errors_raise_before_launch(jz):
     """tests/testbasic.cu:114-249: every incompatible pair is std::invalid_argument."""
-    A, B = jz.CM.ones_(3, 4), jz.CM.ones_(3, 3)
+    A, B, S = jz.CM.ones_(3, 4), jz.CM.ones_(3, 3), jz.CM.ones_(2, 2)
     before = jz.lib().jz_launch_count()
     for fn in (lambda: A + B, lambda: A - B, lambda: A * B, lambda: A / B, lambda: jz.hadmd(A, B),
                lambda: A.T() + B, lambda: A * B.T(), lambda: jz.hadmd(A.T(), B),
-               lambda: jz.hstack([A, jz.CM.ones_(2, 2)]), lambda: jz.vstack([A, B]),
+               lambda: jz.hstack([A, S]), lambda: jz.vstack([A, B]),
                lambda: jz.hstack([]), lambda: jz.vstack([])):
         with pytest.raises(ValueError):
             fn()
