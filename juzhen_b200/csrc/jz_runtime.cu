@@ -103,6 +103,7 @@ struct Pool {
     std::unordered_map<size_t, std::vector<Block>> cached;  // rounded bytes -> free blocks
     std::vector<cudaEvent_t> events;                        // recycled events
     size_t live_bytes = 0, cached_bytes = 0, n_device_allocs = 0, n_hits = 0;
+    bool torn_down = false;  // set by destroy(): late frees from static destructors are then ignored
 
     static size_t round_up(size_t bytes) {
         if (bytes == 0) bytes = 4;  // count==0 -> 1 element (cpp/cumatrix.cuh:71)
@@ -168,8 +169,10 @@ struct Pool {
         if (!p) return JZ_OK;
         std::lock_guard<std::mutex> lk(mu);
         auto it = live.find(p);
-        if (it == live.end())
+        if (it == live.end()) {
+            if (torn_down) return JZ_OK;  // block already returned to the driver by jz_shutdown()
             return fail(JZ_ERR_ARG, "jz_free: pointer %p is not a live pool allocation", p);
+        }
         const size_t rb = it->second;
         live.erase(it);
         live_bytes -= rb;
@@ -185,6 +188,7 @@ struct Pool {
         for (auto& kv : live) cudaFree(kv.first);
         live.clear();
         live_bytes = 0;
+        torn_down = true;
         for (auto ev : events) cudaEventDestroy(ev);
         events.clear();
         return JZ_OK;
