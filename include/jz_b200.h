@@ -154,6 +154,16 @@ int jz_gemm(int transA, int transB, size_t m, size_t n, size_t k, float alpha,
 int jz_gemm_chain(int transA, int transB, size_t m, size_t n, size_t k, float alpha,
                   const float* A, size_t lda, const float* B, size_t ldb,
                   float* C, size_t ldc, const jz_step* steps, int nsteps, int mode, jz_stream_t stream);
+/* Multi-GPU form (column-sharded C = A * B[:, block], then all-gather): the same fused product,
+ * whose epilogue ALSO stores every finished tile into `n_peers` more images of C with the same ldc --
+ * buffers of peer GPUs mapped into this process (CUDA P2P / symmetric memory over NVLink).  The gather
+ * overlaps the math tile by tile; the caller only needs a cross-rank barrier afterwards.  Replaces nothing
+ * in the reference (it has no collectives); the NCCL all-gather variant lives in juzhen_b200/mg.py. */
+#define JZ_MAX_PEERS 7
+int jz_gemm_chain_bcast(int transA, int transB, size_t m, size_t n, size_t k, float alpha,
+                        const float* A, size_t lda, const float* B, size_t ldb,
+                        float* C, size_t ldc, float* const* peer_C, int n_peers,
+                        const jz_step* steps, int nsteps, int mode, jz_stream_t stream);
 /* which kernel family the last jz_gemm used: 0 none, 1 tcgen05, 2 simt, 3 outer/gemv special case */
 int jz_gemm_last_path(void);
 

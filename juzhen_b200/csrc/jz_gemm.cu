@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(256) sgemm_simt_kernel(size_t m, size_t n, siz
     __shared__ ChainParams chain;
     stage_chain(&chain, chain_p, threadIdx.x);
     __syncthreads();
-    __shared__ float As[SBK][SBM + 4];
-    __shared__ float Bs[SBK][SBN + 4];
+    __shared__ __align__(16) float As[SBK][SBM + 4];  // read back as float4
+    __shared__ __align__(16) float Bs[SBK][SBN + 4];
     const int t = threadIdx.x;
     const size_t i0 = size_t(blockIdx.x) * SBM, j0 = size_t(blockIdx.y) * SBN;
     const int tx = t & 15, ty = t >> 4;
@@ -292,6 +292,8 @@ struct GemmArgs {
     size_t ldc;
     unsigned tiles_m, tiles_n;  // in units of (CG*128) x 256 tiles
     int kb_per_chunk;           // k-blocks accumulated inside TMEM before promotion to registers
+    int n_peers;                // additional destinations (peer-GPU images of C, same ldc)
+    float* peers[JZ_MAX_PEERS];
     ChainParams chain;
 };
 
@@ -488,6 +490,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 for (int c = 0; c < 32; c++) {
                     const size_t col = ncol0 + p * 32 + c;
                     if (row_ok && col < args.n) crow[col * args.ldc] = v[c];  // a warp writes 32 consecutive floats
+                }
+                // fused all-gather: the finished values also go straight to every peer GPU's image of C
+                // (P2P stores over NVLink, 128 B per warp per column), tile by tile while other tiles compute
+                for (int q = 0; q < args.n_peers; q++) {
+                    float* prow = args.peers[q] + row;
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const size_t col = ncol0 + p * 32 + c;
+                        if (row_ok && col < args.n) prow[col * args.ldc] = v[c];
+                    }
                 }
             }
         }
@@ -710,7 +722,7 @@ static int launch_tc(const Operand& a, const Operand& b, const GemmArgs& args_in
 
 static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
                    const float* B, size_t ldb, float beta, float* C, size_t ldc, bool split, const ChainParams& chain,
-                   cudaStream_t s) {
+                   float* const* peers, int n_peers, cudaStream_t s) {
     Operand a, b;
     int rc = prepare_operand(a, A, lda, /*kmajor_src=*/ta != 0, m, k, split, s);
     if (rc == JZ_OK) rc = prepare_operand(b, B, ldb, /*kmajor_src=*/tb == 0, n, k, split, s);
@@ -721,6 +733,8 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         args.C = C; args.ldc = ldc;
         args.tiles_m = args.tiles_n = 0;
         args.kb_per_chunk = chunk_kb(split);
+        args.n_peers = n_peers;
+        for (int q = 0; q < JZ_MAX_PEERS; q++) args.peers[q] = q < n_peers ? peers[q] : nullptr;
         args.chain = chain;
         const int cg = pick_cg();
         if (cg == 2) rc = split ? launch_tc<2, true>(a, b, args, s) : launch_tc<2, false>(a, b, args, s);
@@ -734,9 +748,28 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
 
 }  // namespace tc
 
+static int gemm_local(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                      const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain, int mode,
+                      float* const* peers, int n_peers, bool* peers_done, cudaStream_t s);
+
 static int gemm_entry(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
                       const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain, int mode,
-                      cudaStream_t s) {
+                      cudaStream_t s, float* const* peers = nullptr, int n_peers = 0) {
+    if (n_peers < 0 || n_peers > JZ_MAX_PEERS || (n_peers && !peers)) return fail(JZ_ERR_ARG, "jz_gemm: bad peer list");
+    bool peers_done = false;
+    int rc = gemm_local(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, mode, peers, n_peers, &peers_done, s);
+    if (rc != JZ_OK || peers_done || m == 0 || n == 0) return rc;
+    // paths without a fused store (SIMT / rank-1): replicate the finished block with strided P2P copies
+    for (int q = 0; q < n_peers; q++) {
+        rc = jz_copy2d(peers[q], ldc, C, ldc, m, n, 0, s);
+        if (rc != JZ_OK) return rc;
+    }
+    return JZ_OK;
+}
+
+static int gemm_local(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                      const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain, int mode,
+                      float* const* peers, int n_peers, bool* peers_done, cudaStream_t s) {
     if (m == 0 || n == 0) return JZ_OK;
     if (!C) return fail(JZ_ERR_ARG, "jz_gemm: null C");
     if (ldc < m) return fail(JZ_ERR_SHAPE, "jz_gemm: ldc < m");
@@ -768,7 +801,8 @@ static int gemm_entry(int ta, int tb, size_t m, size_t n, size_t k, float alpha,
     if (want_tc && big_enough && fits_i32 && !force_simt) {
         // BF16 mode currently rides the TF32 kernel (a strict accuracy superset of bf16 inputs)
         const bool split = mode == JZ_GEMM_3XTF32;
-        return tc::gemm_tc(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, split, chain, s);
+        *peers_done = true;
+        return tc::gemm_tc(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, split, chain, peers, n_peers, s);
     }
     return launch_simt(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
 }
@@ -794,6 +828,16 @@ int jz_gemm_chain(int transA, int transB, size_t m, size_t n, size_t k, float al
     ChainParams chain;
     if (make_chain(chain, steps, nsteps) != JZ_OK) return fail(JZ_ERR_ARG, "jz_gemm_chain: bad step list");
     return gemm_entry(transA, transB, m, n, k, alpha, A, lda, B, ldb, 0.0f, C, ldc, chain, mode, as_stream(stream));
+}
+
+int jz_gemm_chain_bcast(int transA, int transB, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                        const float* B, size_t ldb, float* C, size_t ldc, float* const* peer_C, int n_peers,
+                        const jz_step* steps, int nsteps, int mode, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    ChainParams chain;
+    if (make_chain(chain, steps, nsteps) != JZ_OK) return fail(JZ_ERR_ARG, "jz_gemm_chain_bcast: bad step list");
+    return gemm_entry(transA, transB, m, n, k, alpha, A, lda, B, ldb, 0.0f, C, ldc, chain, mode, as_stream(stream), peer_C,
+                      n_peers);
 }
 
 }  // extern "C"
