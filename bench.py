@@ -255,6 +255,10 @@ def run_ours(args):
                                              "frac": round(tf / (peak * world), 3), "path": L.jz_gemm_last_path()}
             del a, b, c
 
+    sharded = None
+    if world > 1 and not args.no_gemm:
+        sharded = run_sharded_gemm(jz, L, args, world, rank, stream, timed, pk)
+
     cpu = None
     if rank == 0 and not args.no_cpu:
         cpu = cpu_reference_subprocess(log2n=args.cpu_log2n, steps=1)
@@ -269,12 +273,54 @@ def run_ours(args):
                        "l2": "inputs (1 GiB/operand) larger than L2, no flush", "ops": [n for n, _ in SWEEP],
                        "algorithmic_bytes_per_step": sw.bytes_per_step, "parallelism": f"independent shards x{world}"},
             "frac_of_hbm_peak": round(value / world / pk["hbm_gbs"], 3),
-            "roofline": roofline, "ops": per_op, "gemm": gemm, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "ops": per_op, "gemm": gemm, "sharded_gemm": sharded, "e2e": e2e,
+            "gpu_launches": int(launches),
             "clocks": clk, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sharded_gemm(jz, L, args, world, rank, stream, timed, pk):
+    """BASELINE configs[4]: column-sharded C = log(exp(A*B/n)+1)/5 with the chain fused in the GEMM epilogue,
+    gathered (a) by one NCCL all-gather, (b) by P2P stores from the epilogue (fused) -- strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from juzhen_b200 import mg
+    out = {}
+    for n in args.sharded_n:
+        steps = [("affine", 1.0 / n, 0.0), ("exp",), ("affine", 1.0, 1.0), ("log",), ("affine", FIFTH, 0.0)]
+        a = jz.CM.randn(n, n, seed=21)                       # replicated operand (same seed on every rank)
+        j0, j1 = mg.block_range(n, world, rank)
+        bfull_seed = 22
+        b = jz.CM.randn(n, j1 - j0, seed=bfull_seed, offset=j0 * n)   # this rank's column block of the same B
+        res = {}
+        sums = {}
+        for mode in ("nccl", "fused"):
+            try:
+                g = mg.GpuShardedGemm(jz, n, n, n, steps=steps, gemm_mode=0, mode=mode)
+                fn = lambda: g.run(a.ptr, n, 0, b.ptr, n, stream)  # noqa: E731
+                ms, _ = timed(fn, max(2, args.steps // 3), 1)
+            except Exception as e:  # noqa: BLE001 - report, keep the bench line alive
+                res[mode] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                continue
+            tf = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
+            peak = pk["bf16_tflops"] / 2 / 3 * world
+            chk = g.c_full.view(torch.int32).sum(dtype=torch.int64)
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            sums[mode] = int(chk.item())
+            res[mode] = {"ms": round(ms, 3), "TFLOP/s": round(tf, 1), "frac_of_3xtf32_peak_xN": round(tf / peak, 3),
+                         "replicas_identical": bool(lo.item() == hi.item())}
+            del g
+            torch.cuda.empty_cache()
+        if len(sums) == 2:
+            res["fused_equals_nccl_bitwise"] = sums["nccl"] == sums["fused"]
+        out[str(n)] = res
+        del a, b
+    return out
 
 
 # ---------------------------------------------------------------------------------- reference arm (CPU)
@@ -374,6 +420,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=LOG2N_DEFAULT)
     ap.add_argument("--cpu-log2n", type=int, default=24, dest="cpu_log2n")
     ap.add_argument("--gemm-n", type=int, nargs="*", default=[4096, 8192], dest="gemm_n")
+    ap.add_argument("--sharded-n", type=int, nargs="*", default=[16384, 32768], dest="sharded_n")
     ap.add_argument("--no-gemm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--_cpu_child", action="store_true")
