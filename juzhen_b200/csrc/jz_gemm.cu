@@ -523,54 +523,77 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     if (!isfinite(hi)) { hi = x; lo = 0.0f; }  // keep inf/nan semantics, avoid inf - inf
 }
 
-// source already K-major: src(r, kk) at r*ld + kk ; dst[r*kp + kk]
-template <bool SPLIT>
+// source already K-major: src(r, kk) at r*ld + kk ; dst[r*kp + kk].
+// One thread per quad of k: a 128-bit load, the split, one or two 128-bit stores (VEC), grid-stride.
+template <bool SPLIT, bool VEC>
 __global__ void __launch_bounds__(256) prep_kmajor_kernel(float* hi, float* lo, size_t kp, const float* src, size_t ld,
                                                           size_t rows, size_t k) {
-    for (size_t r = size_t(blockIdx.y) * blockDim.y + threadIdx.y; r < rows; r += size_t(gridDim.y) * blockDim.y) {
-        for (size_t kk = size_t(blockIdx.x) * blockDim.x + threadIdx.x; kk < k; kk += size_t(gridDim.x) * blockDim.x) {
-            const float x = src[r * ld + kk];
-            if (SPLIT) {
-                float h, l;
-                split_tf32(x, h, l);
-                hi[r * kp + kk] = h;
-                lo[r * kp + kk] = l;
-            } else {
-                hi[r * kp + kk] = x;
-            }
+    const size_t kq = kp >> 2;  // quads per row (kp is a multiple of 4)
+    const size_t total = rows * kq;
+    for (size_t idx = size_t(blockIdx.x) * 256 + threadIdx.x; idx < total; idx += size_t(gridDim.x) * 256) {
+        const size_t r = idx / kq, kk = (idx - r * kq) << 2;
+        float x[4];
+        if (VEC && kk + 4 <= k) {
+            const float4 v = *reinterpret_cast<const float4*>(src + r * ld + kk);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) x[i] = kk + i < k ? src[r * ld + kk + i] : 0.0f;
         }
+        float h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (SPLIT) split_tf32(x[i], h[i], l[i]);
+            else h[i] = x[i];
+        }
+        *reinterpret_cast<float4*>(hi + r * kp + kk) = make_float4(h[0], h[1], h[2], h[3]);
+        if (SPLIT) *reinterpret_cast<float4*>(lo + r * kp + kk) = make_float4(l[0], l[1], l[2], l[3]);
     }
 }
 
-// source MN-major: src(r, kk) at kk*ld + r ; dst[r*kp + kk]   (tiled transpose)
-template <bool SPLIT>
+// source MN-major: src(r, kk) at kk*ld + r ; dst[r*kp + kk]   (tiled transpose).
+// 64 x 64 tiles through shared memory; interior tiles use 128-bit accesses on both sides when VEC.
+template <bool SPLIT, bool VEC>
 __global__ void __launch_bounds__(256) prep_transpose_kernel(float* hi, float* lo, size_t kp, const float* src,
                                                              size_t ld, size_t rows, size_t k, size_t tiles_r,
                                                              size_t tiles_k) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[64][65];  // tile[kk][r]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const size_t ntiles = tiles_r * tiles_k;
     for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const size_t tr = t % tiles_r, tk = t / tiles_r;
-        const size_t r0 = tr * 32, k0 = tk * 32;
+        const size_t r0 = tr * 64, k0 = tk * 64;
+        const bool full = VEC && r0 + 64 <= rows && k0 + 64 <= k;
+        if (full) {
 #pragma unroll
-        for (int q = 0; q < 32; q += 8) {
-            const size_t kk = k0 + threadIdx.y + q, r = r0 + threadIdx.x;
-            if (kk < k && r < rows) tile[threadIdx.y + q][threadIdx.x] = src[kk * ld + r];
+            for (int q = 0; q < 4; q++) {
+                const int kl = ty + 16 * q;
+                const float4 v = *reinterpret_cast<const float4*>(src + (k0 + kl) * ld + r0 + 4 * tx);
+                tile[kl][4 * tx + 0] = v.x; tile[kl][4 * tx + 1] = v.y;
+                tile[kl][4 * tx + 2] = v.z; tile[kl][4 * tx + 3] = v.w;
+            }
+        } else {
+            for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+                const int kl = e >> 6, rl = e & 63;
+                tile[kl][rl] = (k0 + kl < k && r0 + rl < rows) ? src[(k0 + kl) * ld + r0 + rl] : 0.0f;
+            }
         }
         __syncthreads();
+        // write: row r of the image, 4 consecutive k per thread (k0 and kp are multiples of 4: always in bounds)
 #pragma unroll
-        for (int q = 0; q < 32; q += 8) {
-            const size_t r = r0 + threadIdx.y + q, kk = k0 + threadIdx.x;
-            if (r < rows && kk < k) {
-                const float x = tile[threadIdx.x][threadIdx.y + q];
-                if (SPLIT) {
-                    float h, l;
-                    split_tf32(x, h, l);
-                    hi[r * kp + kk] = h;
-                    lo[r * kp + kk] = l;
-                } else {
-                    hi[r * kp + kk] = x;
+        for (int q = 0; q < 4; q++) {
+            const int rl = ty + 16 * q;
+            const size_t r = r0 + rl, kk = k0 + 4 * tx;
+            if (r < rows && kk < kp) {
+                float h[4], l[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float x = tile[4 * tx + i][rl];
+                    if (SPLIT) split_tf32(x, h[i], l[i]);
+                    else h[i] = x;
                 }
+                *reinterpret_cast<float4*>(hi + r * kp + kk) = make_float4(h[0], h[1], h[2], h[3]);
+                if (SPLIT) *reinterpret_cast<float4*>(lo + r * kp + kk) = make_float4(l[0], l[1], l[2], l[3]);
             }
         }
         __syncthreads();
@@ -657,23 +680,22 @@ static int prepare_operand(Operand& op, const float* src, size_t ld, bool kmajor
     op.lo = lo;
     op.stride = kp;
     const size_t cap = size_t(ctx().sm_count) * 8;
+    const bool vec = aligned16(src) && ld % 4 == 0;
     if (kmajor_src) {
-        unsigned tx = 1;
-        while (tx < 256 && tx < k) tx <<= 1;
-        const unsigned ty = 256 / tx;
-        size_t gx = ceil_div(k, tx), gy = ceil_div(rows, ty);
-        if (gx > 1024) gx = 1024;
-        if (gy > 32768) gy = 32768;
-        const dim3 grid((unsigned)gx, (unsigned)gy, 1), block(tx, ty, 1);
-        if (split) JZ_LAUNCH((prep_kmajor_kernel<true>), grid, block, 0, s, hi, lo, kp, src, ld, rows, k);
-        else JZ_LAUNCH((prep_kmajor_kernel<false>), grid, block, 0, s, hi, lo, kp, src, ld, rows, k);
+        const size_t blocks = ceil_div(rows * (kp >> 2), size_t(256));
+        const unsigned grid = unsigned(blocks < cap * 2 ? (blocks ? blocks : 1) : cap * 2);
+        if (split && vec) JZ_LAUNCH((prep_kmajor_kernel<true, true>), grid, 256, 0, s, hi, lo, kp, src, ld, rows, k);
+        else if (split) JZ_LAUNCH((prep_kmajor_kernel<true, false>), grid, 256, 0, s, hi, lo, kp, src, ld, rows, k);
+        else if (vec) JZ_LAUNCH((prep_kmajor_kernel<false, true>), grid, 256, 0, s, hi, lo, kp, src, ld, rows, k);
+        else JZ_LAUNCH((prep_kmajor_kernel<false, false>), grid, 256, 0, s, hi, lo, kp, src, ld, rows, k);
     } else {
-        const size_t tiles_r = ceil_div(rows, 32), tiles_k = ceil_div(k, 32);
+        const size_t tiles_r = ceil_div(rows, 64), tiles_k = ceil_div(k, 64);
         const size_t nt = tiles_r * tiles_k;
-        const unsigned grid = unsigned(nt < cap * 4 ? nt : cap * 4);
-        const dim3 block(32, 8, 1);
-        if (split) JZ_LAUNCH((prep_transpose_kernel<true>), grid, block, 0, s, hi, lo, kp, src, ld, rows, k, tiles_r, tiles_k);
-        else JZ_LAUNCH((prep_transpose_kernel<false>), grid, block, 0, s, hi, lo, kp, src, ld, rows, k, tiles_r, tiles_k);
+        const unsigned grid = unsigned(nt < cap ? (nt ? nt : 1) : cap);
+        if (split && vec) JZ_LAUNCH((prep_transpose_kernel<true, true>), grid, 256, 0, s, hi, lo, kp, src, ld, rows, k, tiles_r, tiles_k);
+        else if (split) JZ_LAUNCH((prep_transpose_kernel<true, false>), grid, 256, 0, s, hi, lo, kp, src, ld, rows, k, tiles_r, tiles_k);
+        else if (vec) JZ_LAUNCH((prep_transpose_kernel<false, true>), grid, 256, 0, s, hi, lo, kp, src, ld, rows, k, tiles_r, tiles_k);
+        else JZ_LAUNCH((prep_transpose_kernel<false, false>), grid, 256, 0, s, hi, lo, kp, src, ld, rows, k, tiles_r, tiles_k);
     }
     return JZ_OK;
 }
