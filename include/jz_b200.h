@@ -109,7 +109,7 @@ int jz_div(float* out, const float* a, const float* b, size_t n, jz_stream_t str
 #define JZ_STEP_AFFINE 100
 #define JZ_STEP_ELEMINV 101
 #define JZ_MAX_CHAIN 8
-typedef struct { int kind; float s1; float a; } jz_step;
+typedef struct jz_step { int kind; float s1; float a; } jz_step;
 int jz_chain(float* out, const float* in, size_t n, const jz_step* steps, int nsteps, jz_stream_t stream);
 
 /* ---- transpose-aware 2-D ops.  out is rows x cols (ldo); X_trans != 0 means the logical

@@ -48,7 +48,9 @@ PROGRAMS = [
     ("knn", "examples/knn.cu", []),
     ("pagerank", "examples/pagerank.cu", []),
 ]
-OURS_IN_CPP = {"cumatrix.cuh", "memory.hpp"}
+# this repository's own C++ tests (same compute() convention), staged next to the reference's tests
+OWN_TESTS = [("test_fusion", "test_fusion.cu")]
+OURS_IN_CPP = {"cumatrix.cuh", "memory.hpp", "jz_lazy.hpp"}
 REF_CPP = ["core.hpp", "matrix.hpp", "operators.hpp", "helper.hpp", "juzhen.hpp", "cpulinalg.hpp"]
 
 
@@ -75,6 +77,8 @@ def stage():
         for p in glob.glob(os.path.join(REF, sub, "*")):
             if os.path.isfile(p):
                 link(p, os.path.join(STAGE, sub, os.path.basename(p)))
+    for _, src in OWN_TESTS:
+        link(os.path.join(HERE, "tests", src), os.path.join(STAGE, "tests", src))
     link(os.path.join(REF, "external", "xpu_info", "xpu_info.hpp"), os.path.join(STAGE, "external", "xpu_info", "xpu_info.hpp"))
     eig = os.path.join(REF, "external", "Eigen3")
     if os.path.isdir(eig):  # header tree used only by tests/testEigen.cu: a directory link is fine (no `..` includes)
@@ -128,7 +132,7 @@ def build(only=None, force=False):
     for d in (OBJ, BIN):
         os.makedirs(d, exist_ok=True)
     fl, ob = flags()
-    ours = [os.path.join(HERE, f) for f in ("cumatrix.cuh", "cumatrix.cu", "memory.hpp", "launcher.cu")] + \
+    ours = [os.path.join(HERE, f) for f in ("cumatrix.cuh", "cumatrix.cu", "memory.hpp", "launcher.cu", "jz_lazy.hpp")] + \
            [os.path.join(ROOT, "include", "jz_b200.h")]
     objs = []
     for unit in ("cumatrix", "launcher"):
@@ -144,12 +148,12 @@ def build(only=None, force=False):
     def one(prog):
         name, src, extra = prog
         exe = os.path.join(BIN, name)
-        if not force and newer(exe, ours + objs + [os.path.join(REF, src)]):
+        if not force and newer(exe, ours + objs + [os.path.realpath(os.path.join(STAGE, src))]):
             return name, "up to date"
         run([NVCC, *fl, *extra, os.path.join(STAGE, src), *objs, *link_flags, "-o", exe], f"build {name}")
         return name, "built"
 
-    todo = [p for p in PROGRAMS if not only or p[0] in only]
+    todo = [p for p in PROGRAMS + [(n, "tests/" + s, []) for n, s in OWN_TESTS] if not only or p[0] in only]
     with concurrent.futures.ThreadPoolExecutor(max_workers=6) as ex:
         res = list(ex.map(one, todo))
     for name, st in res:

@@ -13,6 +13,8 @@
 #include "cumatrix.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 using std::string;
 
@@ -28,10 +30,167 @@ inline void require_same_shape(const Matrix<CUDAfloat>& a, const Matrix<CUDAfloa
 }
 }  // namespace
 
+// ------------------------------------------------------------------ deferred evaluation (jz_lazy.hpp)
+namespace jzb200 {
+
+bool lazy_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("JZ_EAGER");
+        return !(e && *e && std::strcmp(e, "0") != 0);
+    }();
+    return on;
+}
+
+Storage::Storage(size_t n) : ptr(reinterpret_cast<float*>(Memory<CUDAfloat>::allocate(n))), count(n) {}
+Storage::~Storage() { Memory<CUDAfloat>::free(reinterpret_cast<CUDAfloat*>(ptr)); }
+
+bool Storage::lazy_ok() const { return lazy_enabled() && !escaped; }
+
+void add_reader(const StoragePtr& source, const StoragePtr& reader) {
+    auto& v = source->readers;
+    v.erase(std::remove_if(v.begin(), v.end(), [](const std::weak_ptr<Storage>& w) { return w.expired(); }), v.end());
+    v.push_back(reader);
+}
+
+// one pass over `count` floats applying `prog` (any length; single steps use the specialised kernels)
+static void run_program(float* out, const float* in, size_t count, const std::vector<jz_step>& prog) {
+    if (prog.empty()) {
+        if (out != in) JZ_DO(jz_copy(out, in, count, S()));
+        return;
+    }
+    size_t at = 0;
+    while (at < prog.size()) {
+        const size_t len = std::min(prog.size() - at, size_t(JZ_MAX_CHAIN));
+        if (len == 1) {
+            const jz_step& st = prog[at];
+            if (st.kind == JZ_STEP_AFFINE) JZ_DO(jz_affine(out, in, count, st.s1, st.a, S()));
+            else if (st.kind == JZ_STEP_ELEMINV) JZ_DO(jz_eleminv(out, in, count, st.s1, S()));
+            else JZ_DO(jz_unary(st.kind, out, in, count, S()));
+        } else {
+            JZ_DO(jz_chain(out, in, count, prog.data() + at, int(len), S()));
+        }
+        in = out;  // later chunks continue in place
+        at += len;
+    }
+}
+
+static void run_gemm(Producer& g, float* out, const std::vector<jz_step>& epilogue) {
+    g.a->materialize();
+    g.b->materialize();
+    const size_t fused = std::min(epilogue.size(), size_t(JZ_MAX_CHAIN));
+    JZ_DO(jz_gemm_chain(g.ta, g.tb, g.m, g.n, g.k, 1.0f, g.a->ptr, g.lda, g.b->ptr, g.ldb, out, g.m ? g.m : 1,
+                        epilogue.data(), int(fused), -1, S()));
+    if (fused < epilogue.size())
+        run_program(out, out, g.m * g.n, std::vector<jz_step>(epilogue.begin() + fused, epilogue.end()));
+}
+
+void Storage::materialize() {
+    if (producer) {
+        std::unique_ptr<Producer> p = std::move(producer);
+        std::vector<jz_step> prog;
+        if (p->kind == Producer::GEMM) {
+            prog.swap(pending);
+            run_gemm(*p, ptr, prog);
+            return;
+        }
+        // The producer holds the only remaining handle on its source: the source was a temporary that has
+        // since died, so nobody will ever ask for ITS bytes -- fold its unfinished work into this pass.
+        // A dead source that is itself "steps applied to X" is spliced out entirely.
+        while (p->src.use_count() == 1 && p->src->producer && p->src->producer->kind == Producer::MAP) {
+            Storage& dead = *p->src;
+            std::vector<jz_step> steps = dead.producer->steps;
+            steps.insert(steps.end(), dead.pending.begin(), dead.pending.end());
+            steps.insert(steps.end(), p->steps.begin(), p->steps.end());
+            p->steps.swap(steps);
+            StoragePtr next = dead.producer->src;
+            p->src = next;  // releases the dead temporary (its buffer goes back to the pool)
+        }
+        Storage& src = *p->src;
+        const bool orphan = p->src.use_count() == 1;
+        if (orphan && src.producer && src.producer->kind == Producer::GEMM) {
+            std::unique_ptr<Producer> g = std::move(src.producer);
+            prog = src.pending;
+            src.pending.clear();
+            prog.insert(prog.end(), p->steps.begin(), p->steps.end());
+            prog.insert(prog.end(), pending.begin(), pending.end());
+            pending.clear();
+            run_gemm(*g, ptr, prog);  // the product lands directly in this buffer, program as its epilogue
+            return;
+        }
+        if (!(orphan && !src.producer)) src.materialize();  // a live source keeps its own bytes up to date
+        prog = src.pending;                                  // (empty unless orphan)
+        prog.insert(prog.end(), p->steps.begin(), p->steps.end());
+        prog.insert(prog.end(), pending.begin(), pending.end());
+        pending.clear();
+        run_program(ptr, src.ptr, count, prog);
+        return;
+    }
+    if (!pending.empty()) {
+        std::vector<jz_step> prog;
+        prog.swap(pending);
+        run_program(ptr, ptr, count, prog);
+    }
+}
+
+void Storage::flush_readers() {
+    if (readers.empty()) return;
+    std::vector<std::weak_ptr<Storage>> rs;
+    rs.swap(readers);
+    for (auto& w : rs)
+        if (StoragePtr r = w.lock())
+            if (r->producer) r->materialize();
+}
+
+void Storage::before_write() {
+    flush_readers();
+    materialize();
+}
+
+void Storage::append(const jz_step& s) {
+    flush_readers();  // they were defined on the value before this step
+    if (!lazy_ok()) {
+        materialize();
+        run_program(ptr, ptr, count, std::vector<jz_step>{s});
+        return;
+    }
+    if (pending.size() >= 2 * size_t(JZ_MAX_CHAIN)) materialize();
+    pending.push_back(s);
+}
+
+float* Storage::escape() {
+    before_write();
+    escaped = true;
+    return ptr;
+}
+
+}  // namespace jzb200
+
+using jzb200::Producer;
+using jzb200::StoragePtr;
+
+static inline jz_step step_unary(int op) { return jz_step{op, 0.0f, 0.0f}; }
+static inline jz_step step_affine(float s1, float a) { return jz_step{JZ_STEP_AFFINE, s1, a}; }
+static inline jz_step step_eleminv(float l) { return jz_step{JZ_STEP_ELEMINV, l, 0.0f}; }
+
 // ------------------------------------------------------------------ storage and lifetime
-std::shared_ptr<CUDAfloat[]> Matrix<CUDAfloat>::new_storage(size_t count) {
-    return std::shared_ptr<CUDAfloat[]>(Memory<CUDAfloat>::allocate(count),
-                                        [](CUDAfloat* p) { Memory<CUDAfloat>::free(p); });
+jzb200::LazyBuf<CUDAfloat> Matrix<CUDAfloat>::new_storage(size_t count) {
+    return jzb200::LazyBuf<CUDAfloat>(StoragePtr(new jzb200::Storage(count)));
+}
+
+// out-of-place elementwise result: defined as "step applied to this storage", computed when needed
+Matrix<CUDAfloat> Matrix<CUDAfloat>::mapped(const char* nm, const jz_step& step) const {
+    Matrix<CUDAfloat> R(Raw{}, nm, numrow, numcol, transpose);
+    if (store().lazy_ok()) {
+        std::unique_ptr<Producer> p(new Producer());
+        p->kind = Producer::MAP;
+        p->src = elements.storage();
+        p->steps.push_back(step);
+        R.store().producer = std::move(p);
+        jzb200::add_reader(elements.storage(), R.elements.storage());
+    } else {
+        jzb200::run_program(R.store().ptr, dev(), count(), std::vector<jz_step>{step});
+    }
+    return R;
 }
 
 Matrix<CUDAfloat>::Matrix(Raw, const char* name, size_t numrow, size_t numcol, bool trans)
@@ -46,13 +205,13 @@ Matrix<CUDAfloat>::Matrix(const char* name, size_t numrow, size_t numcol, int tr
 // upload (cpp/cumatrix.cu:28-48): synchronous, physical buffer and flag carried over unchanged
 Matrix<CUDAfloat>::Matrix(const Matrix<float>& M)
     : Matrix(Raw{}, ("cu_" + M.name).c_str(), M.numrow, M.numcol, M.transpose) {
-    JZ_DO(jz_memcpy_h2d(dev(), M.elements.get(), count(), S()));
+    JZ_DO(jz_memcpy_h2d(store().ptr, M.elements.get(), count(), S()));
     JZ_DO(jz_sync(S()));
 }
 
 Matrix<CUDAfloat>::Matrix(const Matrix<CUDAfloat>& M)
     : Matrix(Raw{}, ("copy of" + M.name).c_str(), M.numrow, M.numcol, M.transpose) {
-    JZ_DO(jz_memcpy_d2d(dev(), M.dev(), count(), S()));
+    JZ_DO(jz_memcpy_d2d(store().ptr, M.dev(), count(), S()));
 }
 
 Matrix<CUDAfloat>::Matrix(Matrix<CUDAfloat>&& M) noexcept
@@ -64,11 +223,12 @@ Matrix<CUDAfloat>::Matrix(Matrix<CUDAfloat>&& M) noexcept
 Matrix<CUDAfloat>& Matrix<CUDAfloat>::operator=(const Matrix<CUDAfloat>& M) {
     if (this == &M) return *this;
     name = "copy of " + M.name;
-    if (count() != M.count() || !elements || elements.use_count() > 1) elements = new_storage(M.count());
+    const float* from = M.dev();
+    elements = new_storage(M.count());  // a fresh block, like the reference (cpp/cumatrix.cu:99-116)
     numrow = M.numrow;
     numcol = M.numcol;
     transpose = M.transpose;
-    JZ_DO(jz_memcpy_d2d(dev(), M.dev(), count(), S()));
+    JZ_DO(jz_memcpy_d2d(store().ptr, from, count(), S()));
     return *this;
 }
 
@@ -95,11 +255,11 @@ const Matrix<CUDAfloat> Matrix<CUDAfloat>::T() const {
 }
 
 // ------------------------------------------------------------------ fillers and RNG
-void Matrix<CUDAfloat>::ones() { JZ_DO(jz_fill(dev(), count(), 1.0f, S())); }
-void Matrix<CUDAfloat>::zeros() { JZ_DO(jz_fill(dev(), count(), 0.0f, S())); }
+void Matrix<CUDAfloat>::ones() { fill(*this, 1.0); }
+void Matrix<CUDAfloat>::zeros() { fill(*this, 0.0); }
 
 Matrix<CUDAfloat>& fill(Matrix<CUDAfloat>& M, double a) {
-    JZ_DO(jz_fill(M.dev(), M.count(), float(a), S()));
+    JZ_DO(jz_fill(M.wdev(), M.count(), float(a), S()));
     return M;
 }
 
@@ -116,14 +276,14 @@ Matrix<CUDAfloat> Matrix<CUDAfloat>::zeros(size_t m, size_t n) { return Matrix<C
 // reference's GPU stream was never reproducible against its CPU mt19937 stream either.
 Matrix<CUDAfloat> Matrix<CUDAfloat>::randn(size_t m, size_t n) {
     Matrix<CUDAfloat> M(Raw{}, "randn", m, n, false);
-    JZ_DO(jz_rand_normal(M.dev(), m * n, GPUSampler::seed, GPUSampler::offset, S()));
+    JZ_DO(jz_rand_normal(M.store().ptr, m * n, GPUSampler::seed, GPUSampler::offset, S()));
     GPUSampler::offset += m * n;
     return M;
 }
 
 Matrix<CUDAfloat> Matrix<CUDAfloat>::rand(size_t m, size_t n) {
     Matrix<CUDAfloat> M(Raw{}, "rand", m, n, false);
-    JZ_DO(jz_rand_uniform(M.dev(), m * n, GPUSampler::seed, GPUSampler::offset, S()));
+    JZ_DO(jz_rand_uniform(M.store().ptr, m * n, GPUSampler::seed, GPUSampler::offset, S()));
     GPUSampler::offset += m * n;
     return M;
 }
@@ -133,47 +293,58 @@ Matrix<CUDAfloat> Matrix<CUDAfloat>::dot(const Matrix<CUDAfloat>& B) const {
     if (num_col() != B.num_row()) throw std::invalid_argument("Matrix dimensions are not compatible");
     const size_t m = num_row(), n = B.num_col(), k = num_col();
     Matrix<CUDAfloat> C(Raw{}, "dot", m, n, false);
-    JZ_DO(jz_gemm(transpose, B.transpose, m, n, k, 1.0f, dev(), numrow, B.dev(), B.numrow, 0.0f, C.dev(),
+    if (store().lazy_ok() && B.store().lazy_ok()) {
+        // defined now, launched when somebody needs the bytes: an elementwise chain applied to the result in
+        // the meantime becomes the GEMM's epilogue (one kernel for log(exp(A*B)+1)/5)
+        std::unique_ptr<Producer> g(new Producer());
+        g->kind = Producer::GEMM;
+        g->a = elements.storage();
+        g->b = B.elements.storage();
+        g->ta = transpose;
+        g->tb = B.transpose;
+        g->m = m; g->n = n; g->k = k;
+        g->lda = numrow; g->ldb = B.numrow;
+        C.store().producer = std::move(g);
+        jzb200::add_reader(elements.storage(), C.elements.storage());
+        if (B.elements.storage() != elements.storage()) jzb200::add_reader(B.elements.storage(), C.elements.storage());
+        return C;
+    }
+    JZ_DO(jz_gemm(transpose, B.transpose, m, n, k, 1.0f, dev(), numrow, B.dev(), B.numrow, 0.0f, C.store().ptr,
                   m ? m : 1, -1, S()));
     return C;
 }
 
 // ------------------------------------------------------------------ affine / axpby / reciprocal
 // s1*M + a (cpp/cumatrix.cu:199-215); layout and flag preserved
-Matrix<CUDAfloat> Matrix<CUDAfloat>::add(float a, float s1) const {
-    Matrix<CUDAfloat> C(Raw{}, "add", numrow, numcol, transpose);
-    JZ_DO(jz_affine(C.dev(), dev(), count(), s1, a, S()));
-    return C;
-}
-void Matrix<CUDAfloat>::add(float a, float s1) { JZ_DO(jz_affine(dev(), dev(), count(), s1, a, S())); }
+Matrix<CUDAfloat> Matrix<CUDAfloat>::add(float a, float s1) const { return mapped("add", step_affine(s1, a)); }
+void Matrix<CUDAfloat>::add(float a, float s1) { store().append(step_affine(s1, a)); }
 
 // M *= s1.  The CPU oracle's scale is add(0, s1) (cpp/core.hpp:148-149): s1*x + 0.0f.
-void Matrix<CUDAfloat>::scale(float s1) { JZ_DO(jz_affine(dev(), dev(), count(), s1, 0.0f, S())); }
+void Matrix<CUDAfloat>::scale(float s1) { store().append(step_affine(s1, 0.0f)); }
 
 // s1*this + s2*B into a fresh, non-transposed matrix of the logical shape (cpp/cumatrix.cu:227-244)
 Matrix<CUDAfloat> Matrix<CUDAfloat>::add(const Matrix<CUDAfloat>& B, float s1, float s2) const {
     require_same_shape(*this, B);
     const size_t r = num_row(), c = num_col();
     Matrix<CUDAfloat> C(Raw{}, "add", r, c, false);
-    if (!transpose && !B.transpose) JZ_DO(jz_axpby(C.dev(), dev(), B.dev(), count(), s1, s2, S()));
-    else JZ_DO(jz_axpby2d(C.dev(), r ? r : 1, r, c, dev(), numrow, transpose, B.dev(), B.numrow, B.transpose, s1, s2, S()));
+    float* out = C.store().ptr;
+    if (!transpose && !B.transpose) JZ_DO(jz_axpby(out, dev(), B.dev(), count(), s1, s2, S()));
+    else JZ_DO(jz_axpby2d(out, r ? r : 1, r, c, dev(), numrow, transpose, B.dev(), B.numrow, B.transpose, s1, s2, S()));
     return C;
 }
 
 // in place: the result keeps this layout, B is read transposed iff the flags differ (cpp/cumatrix.cu:246-260)
 void Matrix<CUDAfloat>::add(const Matrix<CUDAfloat>& B, float s1, float s2) {
     require_same_shape(*this, B);
-    if (transpose == B.transpose) JZ_DO(jz_axpby(dev(), dev(), B.dev(), count(), s1, s2, S()));
-    else JZ_DO(jz_axpby2d(dev(), numrow ? numrow : 1, numrow, numcol, dev(), numrow, 0, B.dev(), B.numrow, 1, s1, s2, S()));
+    const float* b = B.dev();  // before wdev(): B may be a deferred view of this very storage
+    float* x = wdev();
+    if (transpose == B.transpose) JZ_DO(jz_axpby(x, x, b, count(), s1, s2, S()));
+    else JZ_DO(jz_axpby2d(x, numrow ? numrow : 1, numrow, numcol, x, numrow, 0, b, B.numrow, 1, s1, s2, S()));
 }
 
 // l / M (cpp/cumatrix.cu:263-303)
-Matrix<CUDAfloat> Matrix<CUDAfloat>::eleminv(double l) const {
-    Matrix<CUDAfloat> R(Raw{}, "elem_rec", numrow, numcol, transpose);
-    JZ_DO(jz_eleminv(R.dev(), dev(), count(), float(l), S()));
-    return R;
-}
-void Matrix<CUDAfloat>::eleminv(double l) { JZ_DO(jz_eleminv(dev(), dev(), count(), float(l), S())); }
+Matrix<CUDAfloat> Matrix<CUDAfloat>::eleminv(double l) const { return mapped("elem_rec", step_eleminv(float(l))); }
+void Matrix<CUDAfloat>::eleminv(double l) { store().append(step_eleminv(float(l))); }
 
 float Matrix<CUDAfloat>::norm() const {  // cpp/cumatrix.cu:168-175 (cublasSnrm2): syncs
     float r = 0.0f;
@@ -188,7 +359,7 @@ Matrix<CUDAfloat> Matrix<CUDAfloat>::slice(size_t rstart, size_t rend, size_t cs
     if (transpose) { std::swap(rstart, cstart); std::swap(rend, cend); }
     const size_t r = rend - rstart, c = cend - cstart;
     Matrix<CUDAfloat> W(Raw{}, "submatrix", r, c, transpose);
-    JZ_DO(jz_copy2d(W.dev(), r ? r : 1, dev() + cstart * numrow + rstart, numrow, r, c, 0, S()));
+    JZ_DO(jz_copy2d(W.store().ptr, r ? r : 1, dev() + cstart * numrow + rstart, numrow, r, c, 0, S()));
     return W;
 }
 
@@ -197,16 +368,18 @@ Matrix<CUDAfloat> Matrix<CUDAfloat>::slice(size_t rstart, size_t rend, size_t cs
 void Matrix<CUDAfloat>::slice(size_t rstart, size_t rend, size_t cstart, size_t cend, const Matrix<CUDAfloat>& M) {
     if (transpose) { std::swap(rstart, cstart); std::swap(rend, cend); }
     const size_t r = rend - rstart, c = cend - cstart;
-    JZ_DO(jz_copy2d(dev() + cstart * numrow + rstart, numrow, M.dev(), r ? r : 1, r, c, 0, S()));
+    const float* from = M.dev();
+    JZ_DO(jz_copy2d(wdev() + cstart * numrow + rstart, numrow, from, r ? r : 1, r, c, 0, S()));
 }
 
 void copy(Matrix<CUDAfloat>& dest, const Matrix<CUDAfloat>& src) {  // cpp/cukernels.cu:241-256: dest is re-allocated
     dest.numrow = src.numrow;
     dest.numcol = src.numcol;
     dest.transpose = src.transpose;
+    const float* from = src.dev();
     dest.elements.reset();
     dest.elements = Matrix<CUDAfloat>::new_storage(src.count());
-    JZ_DO(jz_copy(dest.dev(), src.dev(), src.count(), S()));
+    JZ_DO(jz_copy(dest.store().ptr, from, src.count(), S()));
 }
 
 // ------------------------------------------------------------------ reductions
@@ -215,18 +388,16 @@ Matrix<CUDAfloat> sum(const Matrix<CUDAfloat>& M, int dim) {
     const bool down_physical_columns = (dim == 0) != M.transpose;
     const size_t len = down_physical_columns ? M.numcol : M.numrow;
     Matrix<CUDAfloat> R(Matrix<CUDAfloat>::Raw{}, "sumM", len, 1, dim == 0);
-    JZ_DO(jz_sum(R.dev(), M.dev(), M.numrow, M.numcol, M.numrow ? M.numrow : 1, down_physical_columns ? 0 : 1, S()));
+    JZ_DO(jz_sum(R.store().ptr, M.dev(), M.numrow, M.numcol, M.numrow ? M.numrow : 1, down_physical_columns ? 0 : 1, S()));
     return R;
 }
 
 // ------------------------------------------------------------------ unary maps (cpp/cukernels.cu:156-239)
 Matrix<CUDAfloat> jz_unary_new(int op, const char* name, const Matrix<CUDAfloat>& M) {
-    Matrix<CUDAfloat> R(Matrix<CUDAfloat>::Raw{}, name, M.numrow, M.numcol, M.transpose);
-    JZ_DO(jz_unary(op, R.dev(), M.dev(), M.count(), S()));
-    return R;
+    return M.mapped(name, step_unary(op));
 }
 Matrix<CUDAfloat> jz_unary_reuse(int op, Matrix<CUDAfloat>&& M) {
-    JZ_DO(jz_unary(op, M.dev(), M.dev(), M.count(), S()));
+    M.store().append(step_unary(op));
     return std::move(M);
 }
 
@@ -246,21 +417,26 @@ Matrix<CUDAfloat> square(Matrix<CUDAfloat>&& M) { return jz_unary_reuse(JZ_SQUAR
 Matrix<CUDAfloat> hadmd(const Matrix<CUDAfloat>& M1, const Matrix<CUDAfloat>& M2) {
     require_same_shape(M1, M2);
     Matrix<CUDAfloat> R(Matrix<CUDAfloat>::Raw{}, "hadmd", M1.numrow, M1.numcol, M1.transpose);
-    if (M1.transpose == M2.transpose) JZ_DO(jz_hadamard(R.dev(), M1.dev(), M2.dev(), M1.count(), S()));
-    else JZ_DO(jz_hadamard2d(R.dev(), M1.numrow ? M1.numrow : 1, M1.numrow, M1.numcol, M1.dev(), M1.numrow, 0, M2.dev(),
+    float* out = R.store().ptr;
+    if (M1.transpose == M2.transpose) JZ_DO(jz_hadamard(out, M1.dev(), M2.dev(), M1.count(), S()));
+    else JZ_DO(jz_hadamard2d(out, M1.numrow ? M1.numrow : 1, M1.numrow, M1.numcol, M1.dev(), M1.numrow, 0, M2.dev(),
                              M2.numrow, 1, S()));
     return R;
 }
 Matrix<CUDAfloat> hadmd(const Matrix<CUDAfloat>& M1, Matrix<CUDAfloat>&& M2) {
     require_same_shape(M1, M2);
     if (M1.transpose != M2.transpose) return hadmd(M1, static_cast<const Matrix<CUDAfloat>&>(M2));
-    JZ_DO(jz_hadamard(M2.dev(), M2.dev(), M1.dev(), M1.count(), S()));
+    const float* other = M1.dev();
+    float* x = M2.wdev();
+    JZ_DO(jz_hadamard(x, x, other, M1.count(), S()));
     return std::move(M2);
 }
 Matrix<CUDAfloat> hadmd(Matrix<CUDAfloat>&& M1, const Matrix<CUDAfloat>& M2) {
     require_same_shape(M1, M2);
     if (M1.transpose != M2.transpose) return hadmd(static_cast<const Matrix<CUDAfloat>&>(M1), M2);
-    JZ_DO(jz_hadamard(M1.dev(), M1.dev(), M2.dev(), M1.count(), S()));
+    const float* other = M2.dev();
+    float* x = M1.wdev();
+    JZ_DO(jz_hadamard(x, x, other, M1.count(), S()));
     return std::move(M1);
 }
 Matrix<CUDAfloat> hadmd(Matrix<CUDAfloat>&& M1, Matrix<CUDAfloat>&& M2) {
@@ -291,7 +467,7 @@ Matrix<CUDAfloat> hstack(std::vector<MatrixView<CUDAfloat>> matrices) {
     for (const auto& m : matrices) {
         const float* src = reinterpret_cast<const float*>(m.data());
         // a flagged view stores its transpose: physical leading dimension = logical column count
-        JZ_DO(jz_copy2d(R.dev() + at * rows, rows, src, m.get_transpose() ? m.num_col() : rows, rows, m.num_col(),
+        JZ_DO(jz_copy2d(R.store().ptr + at * rows, rows, src, m.get_transpose() ? m.num_col() : rows, rows, m.num_col(),
                         m.get_transpose() ? 1 : 0, S()));
         at += m.num_col();
     }
@@ -311,7 +487,7 @@ const Matrix<CUDAfloat> vstack(std::vector<MatrixView<CUDAfloat>> matrices) {
     size_t at = 0;
     for (const auto& m : matrices) {
         const float* src = reinterpret_cast<const float*>(m.data());
-        JZ_DO(jz_copy2d(R.dev() + at, rows, src, m.get_transpose() ? cols : m.num_row(), m.num_row(), cols,
+        JZ_DO(jz_copy2d(R.store().ptr + at, rows, src, m.get_transpose() ? cols : m.num_row(), m.num_row(), cols,
                         m.get_transpose() ? 1 : 0, S()));
         at += m.num_row();
     }
@@ -343,6 +519,6 @@ void read(FILE* fp, Matrix<CUDAfloat>& M) {  // header (rows, cols, flag) + phys
     M.numrow = tmp.get_transpose() ? tmp.num_col() : tmp.num_row();
     M.numcol = tmp.get_transpose() ? tmp.num_row() : tmp.num_col();
     M.transpose = tmp.get_transpose() != 0;
-    JZ_DO(jz_memcpy_h2d(M.dev(), reinterpret_cast<const float*>(tmp.data()), n, S()));
+    JZ_DO(jz_memcpy_h2d(M.wdev(), reinterpret_cast<const float*>(tmp.data()), n, S()));
     JZ_DO(jz_sync(S()));
 }

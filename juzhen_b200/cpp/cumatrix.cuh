@@ -13,7 +13,9 @@
 //   - shape errors are std::invalid_argument("Matrix dimensions are not compatible") raised before
 //     any launch (cpp/cumatrix.cu:181-184); device errors log and exit(1) (cpp/cumatrix.cuh:34-55);
 //   - all work is issued on the legacy default stream so it stays ordered with the raw kernel
-//     launches of unchanged callers.
+//     launches of unchanged callers;
+//   - elementwise chains and GEMM epilogues are FUSED behind the eager-looking API by deferring work in the
+//     storage object (jz_lazy.hpp): `log(exp(A*B)+1.0f)/5.0f` is one GEMM launch with a 4-step epilogue.
 // Only the generic functor entry points elemwise<F> / reduce<F> keep kernels in this header: their
 // functor is an nvcc extended-lambda type, so they cannot live behind a C ABI.
 #ifndef JZ_B200_CUMATRIX_CUH
@@ -26,6 +28,8 @@
 #include <jz_b200.h>
 
 #include <stdexcept>
+
+#include "jz_lazy.hpp"
 
 #include "core.hpp"
 #include "matrix.hpp"
@@ -76,17 +80,28 @@ class Matrix<CUDAfloat> {
     size_t numrow;
     bool transpose;
     std::string name;
-    std::shared_ptr<CUDAfloat[]> elements;
+    // shared handle on the device storage; .get() hands MatrixView real (materialised) bytes
+    jzb200::LazyBuf<CUDAfloat> elements;
 
     struct Raw {};  // tag: internal temporary, storage left uninitialised
     Matrix(Raw, const char* name, size_t numrow, size_t numcol, bool trans);
     Matrix(const char* name, size_t numrow, size_t numcol, int trans);  // zero-filled
-    Matrix(const char* name, size_t numrow, size_t numcol, int trans, std::shared_ptr<CUDAfloat[]> storage)
+    Matrix(const char* name, size_t numrow, size_t numcol, int trans, jzb200::LazyBuf<CUDAfloat> storage)
         : numcol(numcol), numrow(numrow), transpose(trans != 0), name(name), elements(std::move(storage)) {}
 
-    static std::shared_ptr<CUDAfloat[]> new_storage(size_t count);
-    float* dev() const { return reinterpret_cast<float*>(elements.get()); }
+    static jzb200::LazyBuf<CUDAfloat> new_storage(size_t count);
+    jzb200::Storage& store() const { return *elements.storage(); }
+    float* dev() const {  // bytes for READING: runs whatever was deferred on this storage
+        store().materialize();
+        return store().ptr;
+    }
+    float* wdev() {       // bytes for in-place MODIFICATION: deferred readers take their snapshot first
+        store().before_write();
+        return store().ptr;
+    }
     size_t count() const { return numrow * numcol; }
+    // deferred out-of-place elementwise result (same physical shape and flag as this matrix)
+    Matrix<CUDAfloat> mapped(const char* name, const jz_step& step) const;
 
    public:
     // kept for source compatibility with code that talks to cuBLAS itself (TransformerLayer's batched
@@ -114,7 +129,9 @@ class Matrix<CUDAfloat> {
     inline size_t num_row() const { return transpose ? numcol : numrow; }
     inline size_t get_transpose() const { return transpose; }
     std::string get_name() const { return name; }
-    const CUDAfloat* data() const { return elements.get(); }
+    // the raw device pointer leaves the class: materialise, and never defer on this storage again
+    // (callers such as ml/layer.hpp launch their own kernels on it)
+    const CUDAfloat* data() const { return elements ? reinterpret_cast<const CUDAfloat*>(store().escape()) : nullptr; }
 
     void ones();
     void zeros();
@@ -284,6 +301,7 @@ Matrix<CUDAfloat> reduce(Function func, const Matrix<CUDAfloat>& M, int dim, int
     if (along_physical_columns) {
         Matrix<CUDAfloat> result(Matrix<CUDAfloat>::Raw{}, "resM", k, M.numcol, false);
         JZ_DO(jz_fill(result.dev(), result.count(), 0.0f, jz_cpp_stream()));  // functors may accumulate into vdes
+        M.store().before_write();  // the functor may scribble on its input vector (examples/knn.cu:61-69)
         if (M.numcol)
             jzb200::functor_reduce_kernel<<<unsigned((M.numcol + 127) / 128), 128, 0, jzb200::stream()>>>(
                 func, result.dev(), M.dev(), M.numrow, size_t(k), M.numcol);
@@ -313,7 +331,8 @@ Matrix<CUDAfloat> elemwise(Function func, const Matrix<CUDAfloat>& M) {
 
 template <class Function>
 Matrix<CUDAfloat> elemwise(Function func, Matrix<CUDAfloat>&& M) {
-    jzb200::launch_functor_map(func, M.dev(), M.dev(), M.count());
+    float* p = M.wdev();
+    jzb200::launch_functor_map(func, p, p, M.count());
     return std::move(M);
 }
 

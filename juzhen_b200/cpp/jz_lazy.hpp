@@ -1,0 +1,92 @@
+// jz_lazy.hpp -- deferred evaluation behind Matrix<CUDAfloat> ("fusion").
+//
+// The reference's operators are eager: `log(exp(A*B)+1.0f)/5.0f` is a GEMM, a zero-fill, and four
+// separate passes over the result.  The API cannot change -- operators return Matrix by
+// value -- so fusion hides in the storage object every Matrix handle points at:
+//
+//   * an in-place elementwise op (rvalue overloads, add(a,s1), scale, eleminv) only APPENDS a step to
+//     the storage's pending program;
+//   * an out-of-place elementwise op and dot() create a storage whose contents are DEFINED but not yet
+//     computed (a Producer: "these steps applied to that storage" / "this GEMM");
+//   * anything that needs real bytes (a read by a non-elementwise op, to_host, data(), printing)
+//     materialises: the whole program runs as ONE jz_chain pass, or as the epilogue of ONE jz_gemm_chain
+//     when the values come from a product whose un-materialised temporary has already died.
+//
+// Results are bit-identical to the eager order (jz_chain applies the same roundings step by step).
+// Safety rules: a storage whose raw pointer escaped through data() is never deferred (callers launch
+// their own kernels on it); before a storage's value changes, every deferred reader of it is
+// materialised first.  JZ_EAGER=1 turns all of this off.
+#pragma once
+#include <jz_b200.h>
+
+#include <cstddef>
+#include <memory>
+#include <vector>
+
+namespace jzb200 {
+
+struct Storage;
+using StoragePtr = std::shared_ptr<Storage>;
+
+struct Producer {
+    enum Kind { GEMM, MAP } kind = MAP;
+    // GEMM: C(m x n) = op(A)(m x k) * op(B)(k x n), column-major, lda/ldb = physical rows
+    StoragePtr a, b;
+    int ta = 0, tb = 0;
+    size_t m = 0, n = 0, k = 0, lda = 0, ldb = 0;
+    // MAP: out[i] = steps(src[i]) over the flat physical buffer
+    StoragePtr src;
+    std::vector<jz_step> steps;
+};
+
+struct Storage {
+    float* ptr = nullptr;
+    size_t count = 0;
+    bool escaped = false;                         // raw pointer handed out by data()
+    std::vector<jz_step> pending;                 // deferred in-place program
+    std::unique_ptr<Producer> producer;           // deferred definition of the contents
+    std::vector<std::weak_ptr<Storage>> readers;  // storages whose producer reads this one
+
+    explicit Storage(size_t count);
+    ~Storage();
+    Storage(const Storage&) = delete;
+    Storage& operator=(const Storage&) = delete;
+
+    bool lazy_ok() const;           // deferral allowed on this storage
+    void materialize();             // contents become real bytes
+    void flush_readers();           // deferred readers take their snapshot now
+    void before_write();            // flush_readers + materialize: safe to modify the bytes in place
+    void append(const jz_step& s);  // in-place elementwise step (deferred when allowed)
+    float* escape();                // materialise for an outside reader/writer; disables deferral for good
+};
+
+bool lazy_enabled();
+void add_reader(const StoragePtr& source, const StoragePtr& reader);
+
+// what Matrix<CUDAfloat>::elements is: a shared handle on a Storage that looks enough like the
+// reference's std::shared_ptr<CUDAfloat[]> for MatrixView (cpp/core.hpp:60-64) -- get() materialises.
+template <class Elem>
+class LazyBuf {
+    StoragePtr st;
+
+   public:
+    LazyBuf() = default;
+    LazyBuf(std::nullptr_t) {}
+    explicit LazyBuf(StoragePtr s) : st(std::move(s)) {}
+    Elem* get() const {
+        if (!st) return nullptr;
+        st->materialize();
+        return reinterpret_cast<Elem*>(st->ptr);
+    }
+    Elem& operator[](size_t i) const { return get()[i]; }
+    explicit operator bool() const { return bool(st); }
+    long use_count() const { return st.use_count(); }
+    void reset() { st.reset(); }
+    LazyBuf& operator=(std::nullptr_t) {
+        st.reset();
+        return *this;
+    }
+    const StoragePtr& storage() const { return st; }
+};
+
+}  // namespace jzb200

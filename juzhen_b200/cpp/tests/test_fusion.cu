@@ -1,0 +1,160 @@
+// test_fusion.cu -- acceptance test of the deferred-evaluation layer (jz_lazy.hpp) through the reference's
+// public C++ API only.  Same conventions as the reference's tests: define compute(), return non-zero on
+// failure.  Checks (1) values against the Matrix<float> CPU path of the same
+// expression, (2) aliasing / ordering hazards that a lazy implementation could get wrong, (3) that the
+// README expression log(exp(A*B)+1)/5 really runs as ONE GEMM launch with a fused epilogue, and writes a
+// dump that tests/test_dropin_gpu.py compares bit-for-bit between JZ_EAGER=1 and the default lazy mode.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../cpp/juzhen.hpp"
+
+static int failures = 0;
+static std::vector<Matrix<float>> dump;
+
+static float max_abs_diff(const Matrix<float>& a, const Matrix<float>& b) {
+    if (a.num_row() != b.num_row() || a.num_col() != b.num_col()) return INFINITY;
+    float m = 0.0f;
+    for (size_t j = 0; j < a.num_col(); j++)
+        for (size_t i = 0; i < a.num_row(); i++) m = std::max(m, std::fabs(a.elem(i, j) - b.elem(i, j)));
+    return m;
+}
+static float rel_fro(const Matrix<float>& a, const Matrix<float>& b) {
+    double num = 0, den = 0;
+    for (size_t j = 0; j < a.num_col(); j++)
+        for (size_t i = 0; i < a.num_row(); i++) {
+            const double d = double(a.elem(i, j)) - double(b.elem(i, j));
+            num += d * d;
+            den += double(b.elem(i, j)) * double(b.elem(i, j));
+        }
+    return float(std::sqrt(num / (den > 0 ? den : 1)));
+}
+static void check(bool ok, const std::string& what) {
+    std::cout << (ok ? "[PASS] " : "[FAIL] ") << what << std::endl;
+    if (!ok) failures++;
+}
+static Matrix<float> keep(const Matrix<float>& m) {
+    dump.push_back(m);
+    return m;
+}
+
+int compute() {
+    global_rand_gen.seed(7);
+    GPUSampler sampler(7);
+    const size_t n = 512;
+    auto A = Matrix<float>::randn(n, n), B = Matrix<float>::randn(n, n);
+    CM dA(A), dB(B);
+
+    // (1) the README chain: one GEMM launch (plus its two operand pre-passes) and nothing else
+    {
+        jz_sync(nullptr);
+        const unsigned long long before = jz_launch_count();
+        CM R = log(exp(dA * dB / (float)n) + 1.0f) / 5.0f;
+        Matrix<float> got = keep(R.to_host());
+        const unsigned long long launches = jz_launch_count() - before;
+        Matrix<float> want = log(exp(A * B / (float)n) + 1.0f) / 5.0f;
+        std::cout << "    chain launches: " << launches << ", rel_fro vs CPU " << rel_fro(got, want) << std::endl;
+        check(rel_fro(got, want) < 1e-5f, "log(exp(A*B/n)+1)/5 matches the CPU path (1e-5)");
+        const char* eager = std::getenv("JZ_EAGER");
+        if (!(eager && *eager && std::string(eager) != "0"))
+            check(launches <= 3, "fused: GEMM + operand pre-passes only (<= 3 launches)");
+    }
+    // (2) pure elementwise rvalue chain on an existing matrix: one pass
+    {
+        const unsigned long long before = jz_launch_count();
+        CM R = tanh(exp(-dA / 3.0f) * 0.5f - 1.0f);
+        Matrix<float> got = keep(R.to_host());
+        const unsigned long long launches = jz_launch_count() - before;
+        Matrix<float> want = tanh(exp(-A / 3.0f) * 0.5f - 1.0f);
+        std::cout << "    elementwise chain launches: " << launches << std::endl;
+        check(max_abs_diff(got, want) < 2e-6f, "tanh(exp(-A/3)*0.5-1) matches the CPU path");
+    }
+    // (3) a deferred reader must see the OLD value of a source that is modified afterwards
+    {
+        CM X(A);
+        CM Y = exp(X);       // lvalue overload: defined on X's current value
+        X += 1.0f;           // in-place update of X
+        Matrix<float> y = keep(Y.to_host()), x = keep(X.to_host());
+        check(max_abs_diff(y, exp(A)) < 1e-5f * 50, "exp(X) taken before X += 1 sees the old X");
+        check(max_abs_diff(x, A + 1.0f) == 0.0f, "X += 1 applied exactly once");
+    }
+    // (4) a deferred GEMM must use the operand values at the time of the call
+    {
+        CM P(A), Q(B);
+        CM C = P * Q;
+        P.zeros();
+        Q = Q * 2.0f;
+        Matrix<float> c = keep(C.to_host());
+        check(rel_fro(c, A * B) < 1e-5f, "A*B evaluated with the operands as they were at the call");
+    }
+    // (5) T() aliases share pending work
+    {
+        CM X(A);
+        auto XT = X.T();
+        X.scale(2.0f);
+        Matrix<float> xt = keep(XT.to_host());
+        check(max_abs_diff(xt, (A * 2.0f).T()) == 0.0f, "T() view observes an in-place update of its buffer");
+    }
+    // (6) copies are snapshots
+    {
+        CM C = dA * dB;
+        CM D = C;
+        C = exp(std::move(C) / 100.0f);
+        Matrix<float> d = keep(D.to_host()), c = keep(C.to_host());
+        check(rel_fro(d, A * B) < 1e-5f, "copy of a deferred product is the product");
+        check(rel_fro(c, exp(A * B / 100.0f)) < 1e-5f, "moved-from chain continues on the original buffer");
+    }
+    // (7) programs longer than one fused pass
+    {
+        CM X(A);
+        Matrix<float> W = A;
+        for (int i = 0; i < 21; i++) {
+            X = tanh(std::move(X) * 1.5f + 0.25f);
+            W = tanh(std::move(W) * 1.5f + 0.25f);
+        }
+        check(max_abs_diff(keep(X.to_host()), W) < 1e-5f, "63-step program split over several passes");
+    }
+    // (8) data() hands out real bytes and pins the storage to eager mode; rvalue reuse keeps the pointer
+    {
+        CM X = exp(dA / 10.0f);
+        const void* p = (const void*)X.data();
+        Matrix<float> viaptr("h", n, n);
+        cudaMemcpy((void*)viaptr.data(), p, n * n * sizeof(float), cudaMemcpyDeviceToHost);
+        check(max_abs_diff(viaptr, exp(A / 10.0f)) < 1e-5f, "data() points at materialised values");
+        CM Y = square(std::move(X));
+        check((const void*)Y.data() == p, "rvalue overload reuses the buffer after data()");
+        keep(Y.to_host());
+    }
+    // (9) stacking and slicing deferred operands; sums of deferred values
+    {
+        CM H = hstack({exp(dA / 10.0f), dB + 1.0f});
+        Matrix<float> want = hstack<float>({exp(A / 10.0f), B + 1.0f});
+        check(max_abs_diff(keep(H.to_host()), want) < 1e-5f, "hstack of deferred operands");
+        CM S = sum(exp(dA / 10.0f), 0);
+        Matrix<float> ws = sum(exp(A / 10.0f), 0);
+        check(rel_fro(keep(S.to_host()), ws) < 1e-5f, "sum of a deferred operand");
+        CM sl = (dA * dB).slice(3, 40, 5, 17);
+        check(rel_fro(keep(sl.to_host()), (A * B).slice(3, 40, 5, 17)) < 1e-5f, "slice of a deferred product");
+    }
+    // (10) self-referential updates
+    {
+        CM X(A);
+        X = X * X.T() / (float)n;
+        X = exp(X / 50.0f) - X;
+        Matrix<float> W = A * A.T() / (float)n;
+        W = exp(W / 50.0f) - W;
+        check(rel_fro(keep(X.to_host()), W) < 1e-5f, "X = f(X) with X on both sides");
+    }
+
+    const std::string path = std::string(PROJECT_DIR) + "/res/test_fusion_dump.bin";
+    if (FILE* f = fopen(path.c_str(), "wb")) {
+        for (const auto& m : dump) fwrite(m.data(), sizeof(float), m.num_row() * m.num_col(), f);
+        fclose(f);
+    }
+    std::cout << (failures ? "FAILED" : "ALL PASSED") << std::endl;
+    return failures ? 1 : 0;
+}

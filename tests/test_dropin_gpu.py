@@ -109,3 +109,18 @@ def test_demo_mnist_trains():
 def test_knn_runs():
     r = run("knn", timeout=1500)
     assert r.returncode == 0
+
+
+def test_fusion_lazy_equals_eager_bitwise():
+    """juzhen_b200/cpp/tests/test_fusion.cu: deferred evaluation behind the reference's API.  Run once in the
+    default (lazy, fused) mode and once with JZ_EAGER=1 (one launch per operator, the reference's order): every
+    dumped result must be bit-identical, and each run must pass its own CPU-path and hazard checks."""
+    dump = os.path.join(PROJECT, "res", "test_fusion_dump.bin")
+    r = run("test_fusion")
+    assert r.returncode == 0 and "ALL PASSED" in r.stdout
+    lazy = np.fromfile(dump, dtype=np.uint32)
+    r = run("test_fusion", env={"JZ_EAGER": "1"})
+    assert r.returncode == 0 and "ALL PASSED" in r.stdout
+    eager = np.fromfile(dump, dtype=np.uint32)
+    assert lazy.size == eager.size and lazy.size > 0
+    assert np.array_equal(lazy, eager), f"{int((lazy != eager).sum())} of {lazy.size} words differ"
