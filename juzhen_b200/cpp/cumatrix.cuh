@@ -230,13 +230,7 @@ namespace jzb200 {
 inline cudaStream_t stream() { return reinterpret_cast<cudaStream_t>(jz_cpp_stream()); }
 
 inline unsigned stream_grid(size_t tiles) {
-    static int sms = 0;
-    if (!sms) {
-        int cc1 = 0, cc2 = 0;
-        size_t mem = 0;
-        JZ_DO(jz_device_info(&sms, &cc1, &cc2, &mem));
-    }
-    const size_t cap = size_t(sms) * 8;  // 8 CTAs x 256 threads = full occupancy per SM
+    const size_t cap = 0x7fffffffu;  // one 16 KB tile per CTA: measured faster than a persistent grid on B200
     return unsigned(tiles < cap ? (tiles ? tiles : 1) : cap);
 }
 

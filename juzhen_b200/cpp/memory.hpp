@@ -25,6 +25,7 @@ class Memory {
     struct Book {
         std::unordered_map<D *, size_t> in_use;                // block -> element count
         std::unordered_map<size_t, std::vector<D *>> spare;    // element count -> idle blocks
+        bool released = false;                                 // the RAII owner in main() is gone
     };
     // leaked on purpose: matrices with static storage may be released after main() returns
     static Book &book() {
@@ -57,6 +58,7 @@ class Memory {
         Book &b = book();
         auto it = b.in_use.find(p);
         if (it == b.in_use.end()) {
+            if (b.released) return;  // a static-duration matrix outlived main(): its block is already gone
             LOG_ERROR("Memory<{}>::free: unknown block {}", datatype(D), (void *)p);
             ERROR_OUT;
         }
@@ -72,6 +74,7 @@ class Memory {
             for (D *p : kv.second) { delete[] p; elems += kv.first; }
         b.in_use.clear();
         b.spare.clear();
+        b.released = true;
         LOG_INFO("Total {} memory released: {:.2f} MB.", datatype(D), elems * sizeof(D) / 1024.0 / 1024.0);
     }
 };

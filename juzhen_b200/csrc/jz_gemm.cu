@@ -320,7 +320,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ ChainParams s_chain;
+    __shared__ float* s_peers[JZ_MAX_PEERS];
     stage_chain(&s_chain, args.chain, threadIdx.x);  // visible after the setup barrier below
+    if (threadIdx.x == 32) {  // static indices: direct constant-bank reads (a runtime index would spill the array)
+#pragma unroll
+        for (int q = 0; q < JZ_MAX_PEERS; q++) s_peers[q] = args.peers[q];
+    }
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
     // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base slot
@@ -470,35 +475,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
         const size_t row = size_t(m0) + quarter * 32 + lane;
         const bool row_ok = row < args.m;
-        float* crow = args.C + row;
         const size_t ncol0 = size_t(n0) + half * 128;
+        const size_t ldc = args.ldc;
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            if (ncol0 + p * 32 < args.n) {  // warp-uniform
+            const size_t colp = ncol0 + p * 32;
+            if (colp < args.n) {  // warp-uniform
+                const int ncols = args.n - colp < 32 ? int(args.n - colp) : 32;
                 float v[32];
 #pragma unroll
                 for (int c = 0; c < 32; c++) v[c] = args.alpha * acc[p * 32 + c];
-                if (args.beta != 0.0f) {
+                if (args.beta != 0.0f && row_ok) {
+                    const float* src = args.C + row + colp * ldc;  // running pointer: no 32 hoisted addresses
 #pragma unroll
                     for (int c = 0; c < 32; c++) {
-                        const size_t col = ncol0 + p * 32 + c;
-                        if (row_ok && col < args.n) v[c] += args.beta * crow[col * args.ldc];
+                        if (c < ncols) v[c] += args.beta * *src;
+                        src += ldc;
                     }
                 }
                 if (s_chain.n) apply_chain<32>(v, s_chain);
+                // a warp writes 32 consecutive floats (128 B) per column; destination 0 is the local C, the rest
+                // are the peer GPUs' images of C (fused all-gather: P2P stores over NVLink, tile by tile while
+                // other tiles are still computing)
+                if (row_ok) {
+                    for (int d = 0; d <= args.n_peers; d++) {
+                        float* dst = (d == 0 ? args.C : s_peers[d - 1]) + row + colp * ldc;
 #pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    const size_t col = ncol0 + p * 32 + c;
-                    if (row_ok && col < args.n) crow[col * args.ldc] = v[c];  // a warp writes 32 consecutive floats
-                }
-                // fused all-gather: the finished values also go straight to every peer GPU's image of C
-                // (P2P stores over NVLink, 128 B per warp per column), tile by tile while other tiles compute
-                for (int q = 0; q < args.n_peers; q++) {
-                    float* prow = args.peers[q] + row;
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const size_t col = ncol0 + p * 32 + c;
-                        if (row_ok && col < args.n) prow[col * args.ldc] = v[c];
+                        for (int c = 0; c < 32; c++) {
+                            if (c < ncols) *dst = v[c];
+                            dst += ldc;
+                        }
                     }
                 }
             }

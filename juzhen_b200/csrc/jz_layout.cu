@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(kTile* kTileRows) bin2d_t_kernel(float* out, s
 }
 
 static unsigned tile_grid(size_t ntiles) {
-    const size_t cap = size_t(ctx().sm_count) * 8;
+    // 4 resident CTAs per SM measured best for the 64 x 64 transposing tiles (6.05 vs 5.40 TB/s at 8)
+    const size_t cap = size_t(ctx().sm_count) * 4;
     return unsigned(ntiles < cap ? (ntiles ? ntiles : 1) : cap);
 }
 

@@ -21,6 +21,7 @@
 //    across threadIdx.y and across CTAs (grid.y); CTAs write per-chunk partial vectors which
 //    a second pass folds.  Every global read is a full coalesced row segment.
 #include <cfloat>
+#include <cstdlib>
 #include <type_traits>
 
 #include "jz_common.cuh"
@@ -428,6 +429,23 @@ __global__ void nrm2_final_kernel(float* out, const double* partial, int n) {
 template <class Op>
 static int reduce_dim1(float* out, const float* a, size_t rows, size_t cols, size_t ld, cudaStream_t s);
 
+// grid policy knobs (JZ_REDUCE_CAP / JZ_REDUCE_WAVES override them for tuning runs): the streaming kernels
+// measured fastest with one work item per CTA rather than a persistent grid (profiles/r01g_tune_stream.log)
+static size_t stream_cap() {
+    static const size_t v = [] {
+        const char* e = std::getenv("JZ_REDUCE_CAP");
+        return e ? size_t(std::atoll(e)) * size_t(ctx().sm_count) : size_t(0x7fffffff);
+    }();
+    return v;
+}
+static size_t row_waves() {
+    static const size_t v = [] {
+        const char* e = std::getenv("JZ_REDUCE_WAVES");
+        return e ? size_t(std::atoll(e)) : size_t(2);
+    }();
+    return v;
+}
+
 template <class Op>
 static int reduce_dim0(float* out, const float* a, size_t rows, size_t cols, size_t ld, cudaStream_t s) {
     const size_t cap = size_t(ctx().sm_count) * 8;
@@ -443,7 +461,8 @@ static int reduce_dim0(float* out, const float* a, size_t rows, size_t cols, siz
     const size_t warps_wanted = cap * 8;  // one full wave of warps
     if (cols * 4 >= warps_wanted || rows < 32768) {
         const size_t blocks = ceil_div(cols, size_t(8));
-        const unsigned grid = unsigned(blocks < cap ? blocks : cap);
+        const size_t lim = stream_cap();
+        const unsigned grid = unsigned(blocks < lim ? blocks : lim);
         if (vec) JZ_LAUNCH((colreduce_warp_kernel<Op, true>), grid, 256, 0, s, out, a, rows, cols, ld);
         else JZ_LAUNCH((colreduce_warp_kernel<Op, false>), grid, 256, 0, s, out, a, rows, cols, ld);
         return JZ_OK;
@@ -480,7 +499,7 @@ static int reduce_dim1(float* out, const float* a, size_t rows, size_t cols, siz
     const unsigned ty = 256 / tx;
     const size_t gx = ceil_div(row_units, tx);
     // split columns into chunks so the grid has ~2 waves, but keep >= 8*ty columns per chunk
-    size_t nchunks = ceil_div(2 * cap, gx);
+    size_t nchunks = ceil_div(row_waves() * cap, gx);
     const size_t min_cols = size_t(ty) * 8;
     if (nchunks * min_cols > cols) nchunks = cols / min_cols;
     if (nchunks < 1) nchunks = 1;
