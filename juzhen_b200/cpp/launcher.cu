@@ -7,7 +7,9 @@
 // single-pass TF32 instead of the default fp32-accurate 3xTF32; JZ_GEMM_MODE=3xtf32|tf32|fp32|bf16).
 // No cuBLAS handle is created unless the program was built with -DJZ_LEGACY_CUBLAS_HANDLE for code
 // that calls cuBLAS itself (TransformerLayer, ml/layer.hpp:2896-2926); this backend never uses it.
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
 
 #include "../cpp/juzhen.hpp"
@@ -49,9 +51,19 @@ int main() {
         CuBLASErrorCheck(cublasCreate(&Matrix<CUDAfloat>::global_handle));
 #endif
         Memory<CUDAfloat> device_pool;
+        const auto t0 = std::chrono::steady_clock::now();
         { ret = compute(); }
         std::cout << std::endl;
         cudaDeviceSynchronize();
+        if (const char* st = std::getenv("JZ_STATS"); st && *st && *st != '0') {
+            // what the reference's static Profilers cannot show: device-side launch and pool behaviour
+            size_t live = 0, cached = 0, mallocs = 0, hits = 0;
+            jz_pool_stats(&live, &cached, &mallocs, &hits);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            std::cout << "jz_stats: compute() " << ms << " ms, " << jz_launch_count() << " kernel launches, pool: "
+                      << mallocs << " device allocations, " << hits << " reuses, " << (live >> 20) << " MiB live, "
+                      << (cached >> 20) << " MiB cached" << std::endl;
+        }
 #ifdef JZ_LEGACY_CUBLAS_HANDLE
         CuBLASErrorCheck(cublasDestroy(Matrix<CUDAfloat>::global_handle));
 #endif

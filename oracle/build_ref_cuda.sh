@@ -1,0 +1,24 @@
+#!/bin/bash
+# oracle/build_ref_cuda.sh -- builds the UNMODIFIED reference CUDA backend (cuBLAS/cuRAND, its own kernels) for
+# sm_100a from the sources where they lie under /root/reference, as the "existing GPU implementation" bar that
+# SURVEY.md 8(d) asks to report next to ours on the same B200.  Test/measurement infrastructure only: outputs go
+# to oracle/_ref/cuda/ (git-ignored, travels to the GPU box); nothing in the product links or loads them.
+set -e
+REF=${REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$HERE/_ref/cuda
+[ -d "$REF" ] || { echo "reference tree absent: keeping prebuilt $OUT if any"; exit 0; }
+OB=$(ls /opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs/libopenblasp-r0-*.so | head -1)
+mkdir -p "$OUT"
+FLAGS="-std=c++20 -O3 -gencode arch=compute_100a,code=sm_100a --extended-lambda -ccbin /usr/bin/g++ -DCUDA -DLOGGING_OFF -w \
+  -DPROJECT_DIR=\"/root/repo/build/dropin/project\" -I$REF/external/OpenBLAS/include"
+for unit in launcher cumatrix cukernels; do
+  [ "$OUT/$unit.o" -nt "$REF/cpp/$unit.cu" ] || nvcc $FLAGS -c "$REF/cpp/$unit.cu" -o "$OUT/$unit.o" &
+done
+wait
+for prog in demo_gemm demo_mnist; do
+  [ "$OUT/$prog" -nt "$OUT/cumatrix.o" ] || nvcc $FLAGS "$REF/examples/$prog.cu" "$OUT/launcher.o" "$OUT/cumatrix.o" "$OUT/cukernels.o" \
+      -lcublas -lcurand "$OB" -Xlinker --disable-new-dtags -Xlinker -rpath -Xlinker "$(dirname "$OB")" -lpthread -o "$OUT/$prog" &
+done
+wait
+ls -la "$OUT" | grep -v "\.o$"
