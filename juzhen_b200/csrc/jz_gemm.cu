@@ -146,20 +146,20 @@ namespace tc {
 constexpr int BK = 32;               // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;            // tf32: 32 bytes per MMA k-step
 constexpr int TILE_M = 128;          // rows of A per CTA (TMEM lanes)
-constexpr int TILE_N = 256;          // accumulator columns
+// accumulator columns per tile: TN = 256 (default) or 128 (chosen when 256-wide tiles leave a large partial wave)
 constexpr int A_BYTES = TILE_M * BK * 4;  // 16 KB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // TMA warp + MMA warp + 8 epilogue warps
 
-template <int CG> __host__ __device__ constexpr int b_rows() { return CG == 2 ? 128 : 256; }
-template <int CG> __host__ __device__ constexpr int b_bytes() { return b_rows<CG>() * BK * 4; }
-template <int CG, bool SPLIT> __host__ __device__ constexpr int stage_bytes() { return (SPLIT ? 2 : 1) * (A_BYTES + b_bytes<CG>()); }
-template <int CG, bool SPLIT> __host__ __device__ constexpr int num_stages() {
-    constexpr int s = (227 * 1024 - 2048) / stage_bytes<CG, SPLIT>();
-    return s > 6 ? 6 : s;
+template <int CG, int TN> __host__ __device__ constexpr int b_rows() { return TN / CG; }
+template <int CG, int TN> __host__ __device__ constexpr int b_bytes() { return b_rows<CG, TN>() * BK * 4; }
+template <int CG, bool SPLIT, int TN> __host__ __device__ constexpr int stage_bytes() { return (SPLIT ? 2 : 1) * (A_BYTES + b_bytes<CG, TN>()); }
+template <int CG, bool SPLIT, int TN> __host__ __device__ constexpr int num_stages() {
+    constexpr int s = (227 * 1024 - 2048) / stage_bytes<CG, SPLIT, TN>();
+    return s > 8 ? 8 : s;
 }
-template <int CG, bool SPLIT> __host__ __device__ constexpr int smem_bytes() {
-    return num_stages<CG, SPLIT>() * stage_bytes<CG, SPLIT>() + 1024 /*align slack*/ + 256 /*barriers*/;
+template <int CG, bool SPLIT, int TN> __host__ __device__ constexpr int smem_bytes() {
+    return num_stages<CG, SPLIT, TN>() * stage_bytes<CG, SPLIT, TN>() + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -308,14 +308,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
 // length of the chain), so only `kb_per_chunk` k-blocks are chained inside TMEM; the epilogue
 // warps then promote the chunk into fp32 REGISTER accumulators with round-to-nearest adds while
 // the MMA warp is already filling the other TMEM buffer (2 x 256 columns = all 512).
-template <int CG, bool SPLIT>
+template <int CG, bool SPLIT, int TN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const GemmArgs args) {
-    constexpr int STAGES = num_stages<CG, SPLIT>();
-    constexpr int STAGE_BYTES = stage_bytes<CG, SPLIT>();
-    constexpr int B_BYTES = b_bytes<CG>();
+    constexpr int TILE_N = TN;
+    constexpr int HALF_N = TN / 2;       // columns drained by one epilogue warp
+    constexpr int STAGES = num_stages<CG, SPLIT, TN>();
+    constexpr int STAGE_BYTES = stage_bytes<CG, SPLIT, TN>();
+    constexpr int B_BYTES = b_bytes<CG, TN>();
     constexpr uint32_t IDESC = make_idesc_tf32(CG * 128, TILE_N);
 
     extern __shared__ uint8_t smem_raw[];
@@ -353,7 +355,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const unsigned tn = (tile % per_group) / group_m;
     const int m0 = int(tm) * (CG * TILE_M) + int(rank) * TILE_M;  // first row of this CTA
     const int n0 = int(tn) * TILE_N;
-    const int nb0 = n0 + (CG == 2 ? int(rank) * 128 : 0);         // first B row (= C column) this CTA loads
+    const int nb0 = n0 + (CG == 2 ? int(rank) * (TILE_N / 2) : 0);         // first B row (= C column) this CTA loads
     const int num_kb = int((args.k + BK - 1) / BK);
     const int kbc = args.kb_per_chunk;
     const int num_chunks = (num_kb + kbc - 1) / kbc;
@@ -453,17 +455,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int quarter = warp & 3;   // TMEM lane quarter this warp may access (hardware: warp id % 4)
         const int half = e >> 2;        // which 128 of the 256 accumulator columns
         const int lane = threadIdx.x & 31;
-        float acc[128];
+        float acc[HALF_N];
 #pragma unroll
-        for (int i = 0; i < 128; i++) acc[i] = 0.0f;
-        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * 128);
+        for (int i = 0; i < HALF_N; i++) acc[i] = 0.0f;
+        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * HALF_N);
         const uint32_t empty0 = tmem_empty_bar(0) & 0xFEFFFFFFu, empty1 = tmem_empty_bar(1) & 0xFEFFFFFFu;
         for (int chunk = 0; chunk < num_chunks; chunk++) {
             const uint32_t buf = uint32_t(chunk) & 1u;
             mbar_wait(tmem_full_bar(buf), (uint32_t(chunk) >> 1) & 1u);
             tc_fence_after();
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
+            for (int p = 0; p < HALF_N / 32; p++) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(lane_addr + buf * TILE_N + p * 32, r);
 #pragma unroll
@@ -475,10 +477,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
         const size_t row = size_t(m0) + quarter * 32 + lane;
         const bool row_ok = row < args.m;
-        const size_t ncol0 = size_t(n0) + half * 128;
+        const size_t ncol0 = size_t(n0) + half * HALF_N;
         const size_t ldc = args.ldc;
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
+        for (int p = 0; p < HALF_N / 32; p++) {
             const size_t colp = ncol0 + p * 32;
             if (colp < args.n) {  // warp-uniform
                 const int ncols = args.n - colp < 32 ? int(args.n - colp) : 32;
@@ -649,6 +651,27 @@ static int pick_cg() {
     return g_cg;
 }
 
+// Tile width.  A CTA pair owns a 256 x TN tile; MMA time per tile is proportional to TN, so the kernel time is
+// ~ ceil(tiles / pair_slots) * TN.  256-wide tiles are preferred (fewer A re-reads); 128-wide tiles win when the
+// 256-wide tiling ends in a mostly empty wave (4096^2: 256 tiles on 74 pair slots = 3.46 waves -> 4, against
+// 512 half-tiles = 6.92 -> 7 half-waves = 3.5; 1024^2: 16 tiles use 32 of 148 SMs, 32 half-tiles use 64).
+// JZ_GEMM_TN=128|256 forces it.
+static int pick_tile_n(size_t m, size_t n, int cg, bool split) {
+    static const int forced = [] {
+        const char* e = std::getenv("JZ_GEMM_TN");
+        return e ? std::atoi(e) : 0;
+    }();
+    if (cg != 2) return 256;
+    if (forced == 128 || forced == 256) return forced;
+    const size_t slots = size_t(ctx().sm_count) / 2;
+    const size_t tm = ceil_div(m, size_t(256));
+    const size_t t256 = ceil_div(tm * ceil_div(n, size_t(256)), slots) * 256;
+    const size_t t128 = ceil_div(tm * ceil_div(n, size_t(128)), slots) * 128;
+    // measured (profiles/r01l_gemm_sweep.log): narrow tiles re-read A twice as often, which costs single-pass TF32
+    // ~12% at 4096^2 while 3xTF32 (3x the math per byte) gains 1%; both gain 1.7x at 1024^2
+    return t128 * 100 < t256 * (split ? 95 : 70) ? 128 : 256;
+}
+
 // k-blocks (of 32) chained inside TMEM before RN promotion: 3xTF32 keeps the chain short for
 // fp32-grade accuracy; TF32 mode is input-rounding dominated so long chains are harmless.
 static int chunk_kb(bool split) {
@@ -706,24 +729,24 @@ static int prepare_operand(Operand& op, const float* src, size_t ld, bool kmajor
     return JZ_OK;
 }
 
-template <int CG, bool SPLIT>
+template <int CG, bool SPLIT, int TN>
 static int launch_tc(const Operand& a, const Operand& b, const GemmArgs& args_in, cudaStream_t s) {
     GemmArgs args = args_in;
     args.tiles_m = unsigned(ceil_div(args.m, size_t(CG * TILE_M)));
-    args.tiles_n = unsigned(ceil_div(args.n, size_t(TILE_N)));
+    args.tiles_n = unsigned(ceil_div(args.n, size_t(TN)));
     alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
     if ((rc = make_map(&ma_hi, a.hi, args.m, args.k, a.stride, TILE_M)) != JZ_OK) return rc;
-    if ((rc = make_map(&mb_hi, b.hi, args.n, args.k, b.stride, b_rows<CG>())) != JZ_OK) return rc;
+    if ((rc = make_map(&mb_hi, b.hi, args.n, args.k, b.stride, b_rows<CG, TN>())) != JZ_OK) return rc;
     if (SPLIT) {
         if ((rc = make_map(&ma_lo, a.lo, args.m, args.k, a.stride, TILE_M)) != JZ_OK) return rc;
-        if ((rc = make_map(&mb_lo, b.lo, args.n, args.k, b.stride, b_rows<CG>())) != JZ_OK) return rc;
+        if ((rc = make_map(&mb_lo, b.lo, args.n, args.k, b.stride, b_rows<CG, TN>())) != JZ_OK) return rc;
     } else {
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
-    auto kern = gemm_tcgen05_kernel<CG, SPLIT>;
-    constexpr int SMEM = smem_bytes<CG, SPLIT>();
+    auto kern = gemm_tcgen05_kernel<CG, SPLIT, TN>;
+    constexpr int SMEM = smem_bytes<CG, SPLIT, TN>();
     static bool attr_done = false;
     if (!attr_done) {
         JZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -765,8 +788,10 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         for (int q = 0; q < JZ_MAX_PEERS; q++) args.peers[q] = q < n_peers ? peers[q] : nullptr;
         args.chain = chain;
         const int cg = pick_cg();
-        if (cg == 2) rc = split ? launch_tc<2, true>(a, b, args, s) : launch_tc<2, false>(a, b, args, s);
-        else rc = split ? launch_tc<1, true>(a, b, args, s) : launch_tc<1, false>(a, b, args, s);
+        const int tn = pick_tile_n(m, n, cg, split);
+        if (cg == 2 && tn == 256) rc = split ? launch_tc<2, true, 256>(a, b, args, s) : launch_tc<2, false, 256>(a, b, args, s);
+        else if (cg == 2) rc = split ? launch_tc<2, true, 128>(a, b, args, s) : launch_tc<2, false, 128>(a, b, args, s);
+        else rc = split ? launch_tc<1, true, 256>(a, b, args, s) : launch_tc<1, false, 256>(a, b, args, s);
     }
     if (a.owned) ws_free(a.owned, s);
     if (b.owned) ws_free(b.owned, s);
