@@ -9,13 +9,18 @@
 //   * CG = 2: a CTA pair (cluster 2x1x1, cta_group::2) computes one 256 x 256 tile; each CTA
 //     loads its 128 rows of A and its 128-column half of B, the leader issues M=256 N=256 K=8
 //     MMAs that read both CTAs' shared memory.  CG = 1 is the single-SM 128 x 256 variant;
-//   * 3xTF32 (default, fp32 accuracy): operands are pre-split into tf32 "hi" and "lo" parts
-//     (hi = rna_tf32(x), lo = rna_tf32(x - hi)) and every k-block issues
-//     A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same TMEM accumulator;
-//   * both operands are consumed K-major (the canonical UMMA layout): column-major B and
-//     flagged-transpose A already are; the other two cases are re-laid out by the same
-//     pre-pass that does the hi/lo split (a tiled transpose through shared memory).
-//     Pre-pass traffic is O(mk + kn) against O(mnk) math: 6% at 4096^3, 1.5% at 16384^3.
+//   * operands are read by TMA straight from the caller's column-major storage, in either
+//     major: column-major B and flagged-transpose A are K-major (128B swizzle); plain A and
+//     flagged-transpose B are MN-major (32 contiguous rows x 32 k boxes, the 128B swizzle with
+//     32-byte atoms that tf32 MN-major operands require) -- no re-layout pass, no workspace;
+//   * 3xTF32 (default, fp32 accuracy): every k-block issues A_lo*B_hi + A_hi*B_lo + A_hi*B_hi
+//     into the same TMEM accumulator.  kind::tf32 reads fp32 words and drops the low 13
+//     mantissa bits, so the raw tile already IS the "hi" operand (hi = trunc_tf32(x)); the
+//     eight epilogue warps, idle between accumulator drains, compute
+//     lo = rna_tf32(x - trunc_tf32(x)) from each landed tile into a second shared-memory
+//     buffer while the tensor core works on the previous stage (MODE_XFORM).  The older pre-split variant (MODE_PRESPLIT: a pre-pass writes K-major
+//     hi/lo images to workspace, 4 TMA loads per stage) is kept for operands TMA cannot
+//     address in place and for A/B measurement (JZ_GEMM_PRESPLIT=1);
 //
 // Fallback path: a bounds-checked fp32 FMA (SIMT) kernel for shapes TMA cannot address
 // (n = 1001 in tests/testEigen.cu, ld = 10 in the MNIST head), for tiny problems and for
@@ -149,17 +154,22 @@ constexpr int TILE_M = 128;          // rows of A per CTA (TMEM lanes)
 // accumulator columns per tile: TN = 256 (default) or 128 (chosen when 256-wide tiles leave a large partial wave)
 constexpr int A_BYTES = TILE_M * BK * 4;  // 16 KB
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int FIRST_EPI_WARP = 2;
+constexpr int NUM_THREADS = 32 * (FIRST_EPI_WARP + NUM_EPI_WARPS);  // TMA warp + MMA warp + 8 epilogue/transform warps
+constexpr int MODE_TF32 = 0;      // single pass over the raw fp32 tiles
+constexpr int MODE_PRESPLIT = 1;  // 3xTF32, hi/lo images written by a pre-pass (K-major only)
+constexpr int MODE_XFORM = 2;     // 3xTF32, lo computed in shared memory by the transform warps
+constexpr int MN_BOX_BYTES = 32 * BK * 4;  // one MN-major TMA box: 32 contiguous rows x 32 k = 4 KB
 
 template <int CG, int TN> __host__ __device__ constexpr int b_rows() { return TN / CG; }
 template <int CG, int TN> __host__ __device__ constexpr int b_bytes() { return b_rows<CG, TN>() * BK * 4; }
-template <int CG, bool SPLIT, int TN> __host__ __device__ constexpr int stage_bytes() { return (SPLIT ? 2 : 1) * (A_BYTES + b_bytes<CG, TN>()); }
-template <int CG, bool SPLIT, int TN> __host__ __device__ constexpr int num_stages() {
-    constexpr int s = (227 * 1024 - 2048) / stage_bytes<CG, SPLIT, TN>();
+template <int CG, int MODE, int TN> __host__ __device__ constexpr int stage_bytes() { return (MODE != MODE_TF32 ? 2 : 1) * (A_BYTES + b_bytes<CG, TN>()); }
+template <int CG, int MODE, int TN> __host__ __device__ constexpr int num_stages() {
+    constexpr int s = (227 * 1024 - 2048) / stage_bytes<CG, MODE, TN>();
     return s > 8 ? 8 : s;
 }
-template <int CG, bool SPLIT, int TN> __host__ __device__ constexpr int smem_bytes() {
-    return num_stages<CG, SPLIT, TN>() * stage_bytes<CG, SPLIT, TN>() + 1024 /*align slack*/ + 256 /*barriers*/;
+template <int CG, int MODE, int TN> __host__ __device__ constexpr int smem_bytes() {
+    return num_stages<CG, MODE, TN>() * stage_bytes<CG, MODE, TN>() + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -195,10 +205,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
-template <int CG>
+// TO_LEADER: the copy (issued by either CTA of a pair) signals the LEADER CTA's barrier (peer bit cleared);
+// otherwise it signals the issuing CTA's own barrier.
+template <bool TO_LEADER>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    if constexpr (CG == 2) {
-        // both CTAs of the pair signal the LEADER's barrier (peer bit cleared)
+    if constexpr (TO_LEADER) {
         asm volatile(
             "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
             " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
@@ -208,6 +219,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
             " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
             : "memory");
+    }
+}
+// One operand tile of `ROWS` rows x BK k starting at (row0, kc).
+//   K-major source: one box {BK, ROWS}: ROWS rows of 128 B, 128B swizzle.
+//   MN-major source: ROWS/32 boxes {32 rows, BK}: BK rows of 128 B each holding 32 consecutive operand rows
+//   (4 KB per box, 128B swizzle with 32-byte atoms).
+template <bool MN, int ROWS, bool TO_LEADER>
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* map, uint32_t bar, int kc, int row0) {
+    if constexpr (MN) {
+#pragma unroll
+        for (int i = 0; i < ROWS / 32; i++) tma_load_2d<TO_LEADER>(dst + i * MN_BOX_BYTES, map, bar, row0 + 32 * i, kc);
+    } else {
+        tma_load_2d<TO_LEADER>(dst, map, bar, kc, row0);
     }
 }
 template <int CG>
@@ -270,19 +294,34 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+// Shared-memory operand descriptors (sm_100 format: version 1 at bit 46).
+//   K-major tile: rows of 128 B, 128B swizzle (layout type 2), 8-row groups 1024 B apart (SBO); one UMMA_K step
+//   (8 tf32 = 32 B) advances the start address by 32 B inside the swizzled row.
+//   MN-major tile: the tf32-only canonical layout "128B swizzle, 32B atoms" (layout type 1): an atom is 32
+//   consecutive operand rows (128 B) x 4 k; atoms of the next 4 k follow 512 B later (SBO), the next 32 rows
+//   start one TMA box = 4096 B later (LBO); one UMMA_K step covers two k-atoms = 1024 B.
+template <bool MN>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= uint64_t((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units
-    d |= uint64_t(0) << 16;                   // leading byte offset: unused for swizzled K-major
-    d |= uint64_t(1024 >> 4) << 32;           // stride byte offset between 8-row groups
-    d |= uint64_t(1) << 46;                   // descriptor version (sm_100)
-    d |= uint64_t(2) << 61;                   // SWIZZLE_128B
+    if constexpr (MN) {
+        d |= uint64_t(MN_BOX_BYTES >> 4) << 16;   // leading byte offset: between 32-row atoms
+        d |= uint64_t(512 >> 4) << 32;            // stride byte offset: between 4-k atoms
+        d |= uint64_t(1) << 46;
+        d |= uint64_t(1) << 61;                   // SWIZZLE_128B_BASE32B
+    } else {
+        d |= uint64_t(0) << 16;                   // leading byte offset: unused for swizzled K-major
+        d |= uint64_t(1024 >> 4) << 32;           // stride byte offset between 8-row groups
+        d |= uint64_t(1) << 46;
+        d |= uint64_t(2) << 61;                   // SWIZZLE_128B
+    }
     return d;
 }
-// instruction descriptor: tf32 x tf32 -> f32, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+template <bool MN> __host__ __device__ constexpr uint32_t kstep_bytes() { return MN ? 1024u : 32u; }
+// instruction descriptor: tf32 x tf32 -> f32; bit 15 / 16 = A / B is MN-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? 1u << 15 : 0u) | (b_mn ? 1u << 16 : 0u) |
+           (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
 struct GemmArgs {
@@ -300,25 +339,48 @@ struct GemmArgs {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// One (CG*128) x 256 output tile per CTA group.  tmA*/tmB*: [rows][K] K-major tensor maps.
+// lo part of the 3xTF32 split against the hardware's own hi: kind::tf32 drops the low 13 mantissa bits of the
+// fp32 word it reads, so hi = x & 0xFFFFE000 and x - hi is exact in fp32; lo is that remainder rounded to tf32
+// (nearest, ties away: add half an ulp to the magnitude, truncate), so the tensor core reads it unchanged.
+// inf/nan keep their semantics through hi alone (lo = 0 avoids inf - inf).
+__device__ __forceinline__ float tf32_lo_of(float x) {
+    const uint32_t b = __float_as_uint(x);
+    const float d = __fsub_rn(x, __uint_as_float(b & 0xFFFFE000u));
+    const uint32_t r = (__float_as_uint(d) + 0x1000u) & 0xFFFFE000u;
+    return d == d ? __uint_as_float(r) : 0.0f;   // x = inf/nan gives d = nan
+}
+
+// One (CG*128) x TN output tile per CTA group.  tmA*/tmB*: tensor maps of the operands (see make_map).
 //
 // Accumulation is two-level: the tensor core adds each MMA's partial product into the TMEM
 // accumulator with truncation (measured: relative error 6.9e-9 * k, i.e. biased, linear in the
 // length of the chain), so only `kb_per_chunk` k-blocks are chained inside TMEM; the epilogue
 // warps then promote the chunk into fp32 REGISTER accumulators with round-to-nearest adds while
-// the MMA warp is already filling the other TMEM buffer (2 x 256 columns = all 512).
-template <int CG, bool SPLIT, int TN>
+// the MMA warp is already filling the other TMEM buffer (2 x TN columns).
+//
+// Barriers (per smem stage): MODE_TF32 / MODE_PRESPLIT: TMA of both CTAs -> full (leader) -> MMA -> empty (both).
+// MODE_XFORM: TMA -> full (own CTA) -> epilogue warps write lo -> ready (leader) -> MMA -> empty (both).
+template <int CG, int MODE, int TN, bool AMN, bool BMN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const GemmArgs args) {
+    static_assert(MODE != MODE_PRESPLIT || (!AMN && !BMN), "pre-split images are K-major");
+    constexpr bool SPLIT = MODE != MODE_TF32;
+    constexpr bool XFORM = MODE == MODE_XFORM;
+    constexpr bool TO_LEADER = CG == 2 && !XFORM;   // whose `full` barrier the TMA copies signal
     constexpr int TILE_N = TN;
     constexpr int HALF_N = TN / 2;       // columns drained by one epilogue warp
-    constexpr int STAGES = num_stages<CG, SPLIT, TN>();
-    constexpr int STAGE_BYTES = stage_bytes<CG, SPLIT, TN>();
+    constexpr int STAGES = num_stages<CG, MODE, TN>();
+    constexpr int STAGE_BYTES = stage_bytes<CG, MODE, TN>();
+    constexpr int B_ROWS = b_rows<CG, TN>();
     constexpr int B_BYTES = b_bytes<CG, TN>();
-    constexpr uint32_t IDESC = make_idesc_tf32(CG * 128, TILE_N);
+    constexpr int RAW_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t IDESC = make_idesc_tf32(CG * 128, TILE_N, AMN, BMN);
+    constexpr uint32_t KA = kstep_bytes<AMN>(), KB = kstep_bytes<BMN>();
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ ChainParams s_chain;
@@ -330,15 +392,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base slot
+    // barriers: full[STAGES], empty[STAGES], ready[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
-    auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    auto ready_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tmem_full_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
+    auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
     uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr =
-        reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+        reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -363,7 +426,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
-        if (SPLIT) {
+        if (MODE == MODE_PRESPLIT) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
         }
@@ -373,6 +436,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             for (int s = 0; s < STAGES; s++) {
                 mbar_init(full_bar(s), 1);
                 mbar_init(empty_bar(s), 1);
+                mbar_init(ready_bar(s), NUM_EPI_WARPS * CG);       // every transform (= epilogue) warp of the pair
             }
             for (int b = 0; b < 2; b++) {
                 mbar_init(tmem_full_bar(b), 1);
@@ -394,14 +458,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             uint32_t stage = 0, phase = 0;
             for (int kb = 0; kb < num_kb; kb++) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
-                if (leader) mbar_arrive_expect_tx(full_bar(stage), uint32_t(STAGE_BYTES) * CG);
+                if (XFORM) mbar_arrive_expect_tx(full_bar(stage), uint32_t(RAW_BYTES));
+                else if (leader) mbar_arrive_expect_tx(full_bar(stage), uint32_t(STAGE_BYTES) * CG);
                 const uint32_t sa = smem_base + stage * STAGE_BYTES;
                 const int kc = kb * BK;
-                tma_load_2d<CG>(sa, &tmA_hi, full_bar(stage), kc, m0);
-                tma_load_2d<CG>(sa + A_BYTES, &tmB_hi, full_bar(stage), kc, nb0);
-                if (SPLIT) {
-                    tma_load_2d<CG>(sa + A_BYTES + B_BYTES, &tmA_lo, full_bar(stage), kc, m0);
-                    tma_load_2d<CG>(sa + 2 * A_BYTES + B_BYTES, &tmB_lo, full_bar(stage), kc, nb0);
+                tma_load_tile<AMN, TILE_M, TO_LEADER>(sa, &tmA_hi, full_bar(stage), kc, m0);
+                tma_load_tile<BMN, B_ROWS, TO_LEADER>(sa + A_BYTES, &tmB_hi, full_bar(stage), kc, nb0);
+                if (MODE == MODE_PRESPLIT) {
+                    tma_load_tile<false, TILE_M, TO_LEADER>(sa + RAW_BYTES, &tmA_lo, full_bar(stage), kc, m0);
+                    tma_load_tile<false, B_ROWS, TO_LEADER>(sa + RAW_BYTES + A_BYTES, &tmB_lo, full_bar(stage), kc, nb0);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -417,28 +482,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     mbar_wait(tmem_empty_bar(buf), ((uint32_t(chunk) >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                 }
-                mbar_wait(full_bar(stage), phase);
+                mbar_wait(XFORM ? ready_bar(stage) : full_bar(stage), phase);
                 tc_fence_after();
                 const bool chunk_end = (in_chunk == kbc - 1) || (kb == num_kb - 1);
                 if (elect_one()) {
                     const uint32_t d = tmem_base + buf * TILE_N;
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     const uint32_t a_hi = sa, b_hi = sa + A_BYTES;
-                    const uint32_t a_lo = sa + A_BYTES + B_BYTES, b_lo = sa + 2 * A_BYTES + B_BYTES;
+                    const uint32_t a_lo = sa + RAW_BYTES, b_lo = sa + RAW_BYTES + A_BYTES;
                     uint32_t acc = in_chunk == 0 ? 0u : 1u;
                     if (SPLIT) {
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ks++) {
-                            umma_tf32<CG>(d, make_smem_desc(a_lo + ks * 32), make_smem_desc(b_hi + ks * 32), IDESC, acc);
+                            umma_tf32<CG>(d, make_smem_desc<AMN>(a_lo + ks * KA), make_smem_desc<BMN>(b_hi + ks * KB), IDESC, acc);
                             acc = 1u;
                         }
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ks++)
-                            umma_tf32<CG>(d, make_smem_desc(a_hi + ks * 32), make_smem_desc(b_lo + ks * 32), IDESC, 1u);
+                            umma_tf32<CG>(d, make_smem_desc<AMN>(a_hi + ks * KA), make_smem_desc<BMN>(b_lo + ks * KB), IDESC, 1u);
                     }
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ks++) {
-                        umma_tf32<CG>(d, make_smem_desc(a_hi + ks * 32), make_smem_desc(b_hi + ks * 32), IDESC, acc);
+                        umma_tf32<CG>(d, make_smem_desc<AMN>(a_hi + ks * KA), make_smem_desc<BMN>(b_hi + ks * KB), IDESC, acc);
                         acc = 1u;
                     }
                     umma_commit<CG>(empty_bar(stage));                   // frees this smem stage (both CTAs)
@@ -450,30 +515,67 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             }
         }
     } else {
-        // ===================== epilogue: TMEM chunks -> fp32 registers (RN) -> global =====================
-        const int e = warp - 2;
+        // ===================== epilogue warps: lo-part transform of landed stages (MODE_XFORM), =====================
+        // ===================== TMEM chunks -> fp32 registers (RN) -> global                     =====================
+        const int e = warp - FIRST_EPI_WARP;
         const int quarter = warp & 3;   // TMEM lane quarter this warp may access (hardware: warp id % 4)
-        const int half = e >> 2;        // which 128 of the 256 accumulator columns
+        const int half = e >> 2;        // which half of the accumulator columns
         const int lane = threadIdx.x & 31;
         float acc[HALF_N];
 #pragma unroll
         for (int i = 0; i < HALF_N; i++) acc[i] = 0.0f;
         const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * HALF_N);
         const uint32_t empty0 = tmem_empty_bar(0) & 0xFEFFFFFFu, empty1 = tmem_empty_bar(1) & 0xFEFFFFFFu;
-        for (int chunk = 0; chunk < num_chunks; chunk++) {
-            const uint32_t buf = uint32_t(chunk) & 1u;
-            mbar_wait(tmem_full_bar(buf), (uint32_t(chunk) >> 1) & 1u);
-            tc_fence_after();
+        const uint32_t ready0 = ready_bar(0) & 0xFEFFFFFFu;  // on the leader CTA
+        // Transform and drain interleave in ONE instruction stream per warp, ordered so that neither can starve
+        // the other: k-block j reuses the smem stage of k-block j - STAGES, so it cannot land before the MMAs of
+        // k-block j - STAGES have retired; chunk c (k-blocks c*kbc .. (c+1)*kbc - 1) is therefore complete by the
+        // time k-block (c+1)*kbc + STAGES - 1 lands, and is drained right before that k-block is transformed --
+        // after every k-block the chunk itself (and the next chunk's first STAGES - 1) has been handed to the MMA.
+        constexpr int XT = 32 * NUM_EPI_WARPS;            // transform threads per CTA
+        constexpr int N4 = RAW_BYTES / 16;                // float4 words per stage (A tile then B tile, contiguous)
+        constexpr int PER = N4 / XT;                      // float4 words per thread per stage
+        constexpr int BATCH = PER <= 8 ? PER : (PER % 4 == 0 ? 4 : 3);   // all of a thread's loads in flight together
+        static_assert(N4 % XT == 0 && PER % BATCH == 0, "stage size must divide evenly among the transform threads");
+        const int te = threadIdx.x - 32 * FIRST_EPI_WARP;
+        uint32_t stage = 0, phase = 0;
+        int next_drain = 0;
+        const int kb_end = XFORM ? num_kb : 0;
+        for (int kb = 0; kb <= kb_end; kb++) {
+            while (next_drain < num_chunks && (kb >= kb_end || (next_drain + 1) * kbc + STAGES - 1 <= kb)) {
+                const int chunk = next_drain++;
+                const uint32_t buf = uint32_t(chunk) & 1u;
+                mbar_wait(tmem_full_bar(buf), (uint32_t(chunk) >> 1) & 1u);
+                tc_fence_after();
 #pragma unroll
-            for (int p = 0; p < HALF_N / 32; p++) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(lane_addr + buf * TILE_N + p * 32, r);
+                for (int p = 0; p < HALF_N / 32; p++) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(lane_addr + buf * TILE_N + p * 32, r);
 #pragma unroll
-                for (int c = 0; c < 32; c++) acc[p * 32 + c] = __fadd_rn(acc[p * 32 + c], __uint_as_float(r[c]));
+                    for (int c = 0; c < 32; c++) acc[p * 32 + c] = __fadd_rn(acc[p * 32 + c], __uint_as_float(r[c]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(buf ? empty1 : empty0);  // on the leader CTA's barrier
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(buf ? empty1 : empty0);  // on the leader CTA's barrier
+            if (XFORM && kb < kb_end) {
+                mbar_wait(full_bar(stage), phase);
+                const float4* src = reinterpret_cast<const float4*>(gen_base + stage * STAGE_BYTES) + te;
+                float4* dst = reinterpret_cast<float4*>(gen_base + stage * STAGE_BYTES + RAW_BYTES) + te;
+#pragma unroll
+                for (int i0 = 0; i0 < PER; i0 += BATCH) {
+                    float4 v[BATCH];
+#pragma unroll
+                    for (int u = 0; u < BATCH; u++) v[u] = src[(i0 + u) * XT];
+#pragma unroll
+                    for (int u = 0; u < BATCH; u++)
+                        dst[(i0 + u) * XT] = make_float4(tf32_lo_of(v[u].x), tf32_lo_of(v[u].y), tf32_lo_of(v[u].z), tf32_lo_of(v[u].w));
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ready0 + 8u * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
         }
         const size_t row = size_t(m0) + quarter * 32 + lane;
         const bool row_ok = row < args.m;
@@ -628,17 +730,21 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// [rows][k] fp32, row stride `stride_elems`, box = 32 x box_rows, 128B swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const float* base, size_t rows, size_t k, size_t stride_elems, int box_rows) {
+// Tensor map of one operand over its source storage, zero OOB fill.
+//   K-major ([rows][k], row stride `stride_elems`): dims {k, rows}, box {32, box_rows}, 128B swizzle.
+//   MN-major ([k][rows], k stride `stride_elems`): dims {rows, k}, box {32 rows, 32 k}, 128B swizzle / 32B atoms.
+static int make_map(CUtensorMap* map, const float* base, size_t rows, size_t k, size_t stride_elems, int box_rows,
+                    bool mn_major) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(JZ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t dims[2] = {cuuint64_t(k), cuuint64_t(rows)};
+    cuuint64_t dims[2] = {cuuint64_t(mn_major ? rows : k), cuuint64_t(mn_major ? k : rows)};
     cuuint64_t strides[1] = {cuuint64_t(stride_elems) * sizeof(float)};
-    cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(box_rows)};
+    cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(mn_major ? BK : box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(JZ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
     return JZ_OK;
 }
@@ -650,13 +756,18 @@ static int pick_cg() {
     g_cg = (e && e[0] == '1') ? 1 : 2;
     return g_cg;
 }
+static bool env_flag(const char* name) {
+    const char* e = std::getenv(name);
+    return e && e[0] && e[0] != '0';
+}
 
-// Tile width.  A CTA pair owns a 256 x TN tile; MMA time per tile is proportional to TN, so the kernel time is
-// ~ ceil(tiles / pair_slots) * TN.  256-wide tiles are preferred (fewer A re-reads); 128-wide tiles win when the
-// 256-wide tiling ends in a mostly empty wave (4096^2: 256 tiles on 74 pair slots = 3.46 waves -> 4, against
-// 512 half-tiles = 6.92 -> 7 half-waves = 3.5; 1024^2: 16 tiles use 32 of 148 SMs, 32 half-tiles use 64).
-// JZ_GEMM_TN=128|256 forces it.
-static int pick_tile_n(size_t m, size_t n, int cg, bool split) {
+// Tile width.  A CTA pair owns a 256 x TN tile.  256-wide tiles are preferred: per k-block the A tile is loaded
+// (and, in 3xTF32, transformed) once per tile whatever its width, so a 128-wide tile costs well over half a
+// 256-wide one (measured, profiles/r01o_gemm_sweep.log: 2048^2 3xTF32 66 us with 64 wide tiles in one wave against
+// 97 us with 128 narrow tiles in two; 4096^2 0.52 against 0.62 ms although the narrow tiling has the fuller last
+// wave).  Narrow tiles only pay when the wide tiling cannot occupy half the SM pairs (1024^2: 16 tiles on 74 pair
+// slots).  JZ_GEMM_TN=128|256 forces it.
+static int pick_tile_n(size_t m, size_t n, int cg) {
     static const int forced = [] {
         const char* e = std::getenv("JZ_GEMM_TN");
         return e ? std::atoi(e) : 0;
@@ -664,12 +775,8 @@ static int pick_tile_n(size_t m, size_t n, int cg, bool split) {
     if (cg != 2) return 256;
     if (forced == 128 || forced == 256) return forced;
     const size_t slots = size_t(ctx().sm_count) / 2;
-    const size_t tm = ceil_div(m, size_t(256));
-    const size_t t256 = ceil_div(tm * ceil_div(n, size_t(256)), slots) * 256;
-    const size_t t128 = ceil_div(tm * ceil_div(n, size_t(128)), slots) * 128;
-    // measured (profiles/r01l_gemm_sweep.log): narrow tiles re-read A twice as often, which costs single-pass TF32
-    // ~12% at 4096^2 while 3xTF32 (3x the math per byte) gains 1%; both gain 1.7x at 1024^2
-    return t128 * 100 < t256 * (split ? 95 : 70) ? 128 : 256;
+    const size_t t256 = ceil_div(m, size_t(256)) * ceil_div(n, size_t(256));
+    return t256 * 2 <= slots ? 128 : 256;
 }
 
 // k-blocks (of 32) chained inside TMEM before RN promotion: 3xTF32 keeps the chain short for
@@ -685,20 +792,27 @@ static int chunk_kb(bool split) {
 }
 
 struct Operand {
-    const float* hi = nullptr;
-    const float* lo = nullptr;
-    size_t stride = 0;     // elements between consecutive rows of the K-major image
-    void* owned = nullptr; // workspace to release
+    const float* hi = nullptr;   // raw fp32 (MODE_TF32 / MODE_XFORM) or the tf32 hi image (MODE_PRESPLIT)
+    const float* lo = nullptr;   // MODE_PRESPLIT only
+    size_t stride = 0;           // elements between consecutive rows (K-major) / consecutive k (MN-major)
+    bool mn = false;             // MN-major: element (r, kk) at kk*stride + r
+    void* owned = nullptr;       // workspace to release
 };
 
-// Build the K-major image(s) of an operand.  kmajor_src: src(r,kk) at r*ld+kk, else at kk*ld+r.
+// Describe an operand for the kernel.  kmajor_src: src(r,kk) at r*ld+kk, else at kk*ld+r.
+// In place (no copy, either major) whenever TMA can address the source: 16-byte aligned base and row pitch.
+// Otherwise -- or when `presplit` asks for hi/lo images -- a pre-pass writes K-major image(s) to workspace.
 static int prepare_operand(Operand& op, const float* src, size_t ld, bool kmajor_src, size_t rows, size_t k,
-                           bool split, cudaStream_t s) {
-    if (!split && kmajor_src && ld % 4 == 0 && aligned16(src)) {  // TF32 mode: TMA straight from the source
+                           bool presplit, cudaStream_t s) {
+    static const bool no_mn = env_flag("JZ_GEMM_NO_MN");   // debugging: never consume MN-major sources in place
+    const bool tma_ok = ld % 4 == 0 && aligned16(src);
+    if (!presplit && tma_ok && (kmajor_src || !no_mn)) {
         op.hi = src;
         op.stride = ld;
+        op.mn = !kmajor_src;
         return JZ_OK;
     }
+    const bool split = presplit;
     const size_t kp = (k + 3) & ~size_t(3);
     const size_t elems = rows * kp;
     int rc = ws_alloc(&op.owned, (split ? 2 : 1) * elems * sizeof(float), s);
@@ -708,8 +822,9 @@ static int prepare_operand(Operand& op, const float* src, size_t ld, bool kmajor
     op.hi = hi;
     op.lo = lo;
     op.stride = kp;
+    op.mn = false;
     const size_t cap = size_t(ctx().sm_count) * 8;
-    const bool vec = aligned16(src) && ld % 4 == 0;
+    const bool vec = tma_ok;
     if (kmajor_src) {
         const size_t blocks = ceil_div(rows * (kp >> 2), size_t(256));
         const unsigned grid = unsigned(blocks < cap * 2 ? (blocks ? blocks : 1) : cap * 2);
@@ -729,24 +844,24 @@ static int prepare_operand(Operand& op, const float* src, size_t ld, bool kmajor
     return JZ_OK;
 }
 
-template <int CG, bool SPLIT, int TN>
+template <int CG, int MODE, int TN, bool AMN, bool BMN>
 static int launch_tc(const Operand& a, const Operand& b, const GemmArgs& args_in, cudaStream_t s) {
     GemmArgs args = args_in;
     args.tiles_m = unsigned(ceil_div(args.m, size_t(CG * TILE_M)));
     args.tiles_n = unsigned(ceil_div(args.n, size_t(TN)));
     alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = make_map(&ma_hi, a.hi, args.m, args.k, a.stride, TILE_M)) != JZ_OK) return rc;
-    if ((rc = make_map(&mb_hi, b.hi, args.n, args.k, b.stride, b_rows<CG, TN>())) != JZ_OK) return rc;
-    if (SPLIT) {
-        if ((rc = make_map(&ma_lo, a.lo, args.m, args.k, a.stride, TILE_M)) != JZ_OK) return rc;
-        if ((rc = make_map(&mb_lo, b.lo, args.n, args.k, b.stride, b_rows<CG, TN>())) != JZ_OK) return rc;
+    if ((rc = make_map(&ma_hi, a.hi, args.m, args.k, a.stride, TILE_M, AMN)) != JZ_OK) return rc;
+    if ((rc = make_map(&mb_hi, b.hi, args.n, args.k, b.stride, b_rows<CG, TN>(), BMN)) != JZ_OK) return rc;
+    if (MODE == MODE_PRESPLIT) {
+        if ((rc = make_map(&ma_lo, a.lo, args.m, args.k, a.stride, TILE_M, false)) != JZ_OK) return rc;
+        if ((rc = make_map(&mb_lo, b.lo, args.n, args.k, b.stride, b_rows<CG, TN>(), false)) != JZ_OK) return rc;
     } else {
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
-    auto kern = gemm_tcgen05_kernel<CG, SPLIT, TN>;
-    constexpr int SMEM = smem_bytes<CG, SPLIT, TN>();
+    auto kern = gemm_tcgen05_kernel<CG, MODE, TN, AMN, BMN>;
+    constexpr int SMEM = smem_bytes<CG, MODE, TN>();
     static bool attr_done = false;
     if (!attr_done) {
         JZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -771,12 +886,31 @@ static int launch_tc(const Operand& a, const Operand& b, const GemmArgs& args_in
     return JZ_OK;
 }
 
+// operand majors are compile-time (they select TMA box shapes and descriptor layouts)
+template <int CG, int MODE, int TN>
+static int launch_tc_major(const Operand& a, const Operand& b, const GemmArgs& args, cudaStream_t s) {
+    if constexpr (MODE == MODE_PRESPLIT) {
+        return launch_tc<CG, MODE, TN, false, false>(a, b, args, s);
+    } else {
+        if (a.mn) return b.mn ? launch_tc<CG, MODE, TN, true, true>(a, b, args, s) : launch_tc<CG, MODE, TN, true, false>(a, b, args, s);
+        return b.mn ? launch_tc<CG, MODE, TN, false, true>(a, b, args, s) : launch_tc<CG, MODE, TN, false, false>(a, b, args, s);
+    }
+}
+template <int MODE>
+static int launch_tc_shape(int cg, int tn, const Operand& a, const Operand& b, const GemmArgs& args, cudaStream_t s) {
+    if (cg == 2 && tn == 256) return launch_tc_major<2, MODE, 256>(a, b, args, s);
+    if (cg == 2) return launch_tc_major<2, MODE, 128>(a, b, args, s);
+    return launch_tc_major<1, MODE, 256>(a, b, args, s);
+}
+
 static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
                    const float* B, size_t ldb, float beta, float* C, size_t ldc, bool split, const ChainParams& chain,
                    float* const* peers, int n_peers, cudaStream_t s) {
+    static const bool force_presplit = env_flag("JZ_GEMM_PRESPLIT");   // A/B measurement of the older variant
+    const bool presplit = split && force_presplit;
     Operand a, b;
-    int rc = prepare_operand(a, A, lda, /*kmajor_src=*/ta != 0, m, k, split, s);
-    if (rc == JZ_OK) rc = prepare_operand(b, B, ldb, /*kmajor_src=*/tb == 0, n, k, split, s);
+    int rc = prepare_operand(a, A, lda, /*kmajor_src=*/ta != 0, m, k, presplit, s);
+    if (rc == JZ_OK) rc = prepare_operand(b, B, ldb, /*kmajor_src=*/tb == 0, n, k, presplit, s);
     if (rc == JZ_OK) {
         GemmArgs args;
         args.m = m; args.n = n; args.k = k;
@@ -788,10 +922,10 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         for (int q = 0; q < JZ_MAX_PEERS; q++) args.peers[q] = q < n_peers ? peers[q] : nullptr;
         args.chain = chain;
         const int cg = pick_cg();
-        const int tn = pick_tile_n(m, n, cg, split);
-        if (cg == 2 && tn == 256) rc = split ? launch_tc<2, true, 256>(a, b, args, s) : launch_tc<2, false, 256>(a, b, args, s);
-        else if (cg == 2) rc = split ? launch_tc<2, true, 128>(a, b, args, s) : launch_tc<2, false, 128>(a, b, args, s);
-        else rc = split ? launch_tc<1, true, 256>(a, b, args, s) : launch_tc<1, false, 256>(a, b, args, s);
+        const int tn = pick_tile_n(m, n, cg);
+        if (!split) rc = launch_tc_shape<MODE_TF32>(cg, tn, a, b, args, s);
+        else if (presplit) rc = launch_tc_shape<MODE_PRESPLIT>(cg, tn, a, b, args, s);
+        else rc = launch_tc_shape<MODE_XFORM>(cg, tn, a, b, args, s);
     }
     if (a.owned) ws_free(a.owned, s);
     if (b.owned) ws_free(b.owned, s);
