@@ -90,6 +90,10 @@ int jz_pool_stats(size_t* live_bytes, size_t* cached_bytes, size_t* n_device_all
 /* ---- copies (replaces the sync cudaMemcpy calls, cpp/cumatrix.cu:42,77,108,155) */
 int jz_memcpy_h2d(float* dst_dev, const float* src_host, size_t count, jz_stream_t stream);
 int jz_memcpy_d2h(float* dst_host, const float* src_dev, size_t count, jz_stream_t stream); /* syncs stream */
+/* upload from pageable memory through a pinned staging ring: src_host may be reused on return, and the host does
+   not wait for earlier work in the stream (the per-step batch upload of examples/demo_mnist.cu:108-109, which the
+   reference does with a synchronous cudaMemcpy, cpp/cumatrix.cu:28-48) */
+int jz_upload(float* dst_dev, const float* src_host, size_t count, jz_stream_t stream);
 int jz_memcpy_d2d(float* dst_dev, const float* src_dev, size_t count, jz_stream_t stream);
 
 /* ---- flat elementwise maps over n contiguous floats (out may alias in) */

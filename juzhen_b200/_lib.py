@@ -52,6 +52,7 @@ _SIGS = {
     "jz_pool_trim": (c_int, []),
     "jz_pool_stats": (c_int, [POINTER(c_size_t)] * 4),
     "jz_memcpy_h2d": (c_int, [_F, _F, c_size_t, _S]),
+    "jz_upload": (c_int, [_F, _F, c_size_t, _S]),
     "jz_memcpy_d2h": (c_int, [_F, _F, c_size_t, _S]),
     "jz_memcpy_d2d": (c_int, [_F, _F, c_size_t, _S]),
     "jz_fill": (c_int, [_F, c_size_t, c_float, _S]),

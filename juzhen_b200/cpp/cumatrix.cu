@@ -84,7 +84,17 @@ static void run_gemm(Producer& g, float* out, const std::vector<jz_step>& epilog
         run_program(out, out, g.m * g.n, std::vector<jz_step>(epilogue.begin() + fused, epilogue.end()));
 }
 
+static void run_generator(const Producer& p, float* out, size_t count) {
+    if (p.kind == Producer::FILL) JZ_DO(jz_fill(out, count, p.value, S()));
+    else if (p.normal) JZ_DO(jz_rand_normal(out, count, p.seed, p.offset, S()));
+    else JZ_DO(jz_rand_uniform(out, count, p.seed, p.offset, S()));
+}
+
 void Storage::materialize() {
+    if (producer && (producer->kind == Producer::FILL || producer->kind == Producer::RAND)) {
+        std::unique_ptr<Producer> p = std::move(producer);
+        run_generator(*p, ptr, count);   // then the pending in-place program, below
+    }
     if (producer) {
         std::unique_ptr<Producer> p = std::move(producer);
         std::vector<jz_step> prog;
@@ -157,6 +167,17 @@ void Storage::append(const jz_step& s) {
     pending.push_back(s);
 }
 
+void Storage::define(std::unique_ptr<Producer> p) {
+    flush_readers();   // deferred readers were defined on the old value
+    pending.clear();   // ... which nobody else can ask for any more
+    producer.reset();
+    if (lazy_ok()) {
+        producer = std::move(p);
+        return;
+    }
+    run_generator(*p, ptr, count);
+}
+
 float* Storage::escape() {
     before_write();
     escaped = true;
@@ -205,8 +226,9 @@ Matrix<CUDAfloat>::Matrix(const char* name, size_t numrow, size_t numcol, int tr
 // upload (cpp/cumatrix.cu:28-48): synchronous, physical buffer and flag carried over unchanged
 Matrix<CUDAfloat>::Matrix(const Matrix<float>& M)
     : Matrix(Raw{}, ("cu_" + M.name).c_str(), M.numrow, M.numcol, M.transpose) {
-    JZ_DO(jz_memcpy_h2d(store().ptr, M.elements.get(), count(), S()));
-    JZ_DO(jz_sync(S()));
+    // staged through pinned memory: M's buffer is free again on return (as after the reference's synchronous
+    // cudaMemcpy) but the host does not wait for the device to drain first
+    JZ_DO(jz_upload(store().ptr, M.elements.get(), count(), S()));
 }
 
 Matrix<CUDAfloat>::Matrix(const Matrix<CUDAfloat>& M)
@@ -259,7 +281,10 @@ void Matrix<CUDAfloat>::ones() { fill(*this, 1.0); }
 void Matrix<CUDAfloat>::zeros() { fill(*this, 0.0); }
 
 Matrix<CUDAfloat>& fill(Matrix<CUDAfloat>& M, double a) {
-    JZ_DO(jz_fill(M.wdev(), M.count(), float(a), S()));
+    std::unique_ptr<Producer> p(new Producer());
+    p->kind = Producer::FILL;
+    p->value = float(a);
+    M.store().define(std::move(p));
     return M;
 }
 
@@ -276,14 +301,23 @@ Matrix<CUDAfloat> Matrix<CUDAfloat>::zeros(size_t m, size_t n) { return Matrix<C
 // reference's GPU stream was never reproducible against its CPU mt19937 stream either.
 Matrix<CUDAfloat> Matrix<CUDAfloat>::randn(size_t m, size_t n) {
     Matrix<CUDAfloat> M(Raw{}, "randn", m, n, false);
-    JZ_DO(jz_rand_normal(M.store().ptr, m * n, GPUSampler::seed, GPUSampler::offset, S()));
+    std::unique_ptr<Producer> p(new Producer());
+    p->kind = Producer::RAND;
+    p->normal = true;
+    p->seed = GPUSampler::seed;
+    p->offset = GPUSampler::offset;
+    M.store().define(std::move(p));
     GPUSampler::offset += m * n;
     return M;
 }
 
 Matrix<CUDAfloat> Matrix<CUDAfloat>::rand(size_t m, size_t n) {
     Matrix<CUDAfloat> M(Raw{}, "rand", m, n, false);
-    JZ_DO(jz_rand_uniform(M.store().ptr, m * n, GPUSampler::seed, GPUSampler::offset, S()));
+    std::unique_ptr<Producer> p(new Producer());
+    p->kind = Producer::RAND;
+    p->seed = GPUSampler::seed;
+    p->offset = GPUSampler::offset;
+    M.store().define(std::move(p));
     GPUSampler::offset += m * n;
     return M;
 }

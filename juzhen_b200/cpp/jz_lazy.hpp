@@ -8,6 +8,9 @@
 //     the storage's pending program;
 //   * an out-of-place elementwise op and dot() create a storage whose contents are DEFINED but not yet
 //     computed (a Producer: "these steps applied to that storage" / "this GEMM");
+//   * fills (the zero-init contract of the public constructor, ones()) and random draws are deferred too: a
+//     matrix that is constructed and then replaced or destroyed without being read -- every dummy weight,
+//     bias and Adam buffer of the per-iteration LogisticLayer in examples/demo_mnist.cu:118 -- costs no launch;
 //   * anything that needs real bytes (a read by a non-elementwise op, to_host, data(), printing)
 //     materialises: the whole program runs as ONE jz_chain pass, or as the epilogue of ONE jz_gemm_chain
 //     when the values come from a product whose un-materialised temporary has already died.
@@ -29,7 +32,7 @@ struct Storage;
 using StoragePtr = std::shared_ptr<Storage>;
 
 struct Producer {
-    enum Kind { GEMM, MAP } kind = MAP;
+    enum Kind { GEMM, MAP, FILL, RAND } kind = MAP;
     // GEMM: C(m x n) = op(A)(m x k) * op(B)(k x n), column-major, lda/ldb = physical rows
     StoragePtr a, b;
     int ta = 0, tb = 0;
@@ -37,6 +40,11 @@ struct Producer {
     // MAP: out[i] = steps(src[i]) over the flat physical buffer
     StoragePtr src;
     std::vector<jz_step> steps;
+    // FILL: every element = value.  RAND: counter-based stream (seed, offset) fixed when the matrix was made,
+    // so the values do not depend on when -- or whether -- the kernel runs.
+    float value = 0.0f;
+    bool normal = false;
+    unsigned long long seed = 0, offset = 0;
 };
 
 struct Storage {
@@ -57,6 +65,7 @@ struct Storage {
     void flush_readers();           // deferred readers take their snapshot now
     void before_write();            // flush_readers + materialize: safe to modify the bytes in place
     void append(const jz_step& s);  // in-place elementwise step (deferred when allowed)
+    void define(std::unique_ptr<Producer> p);  // the WHOLE buffer is redefined (fill / random draw): old work is dropped
     float* escape();                // materialise for an outside reader/writer; disables deferral for good
 };
 

@@ -150,6 +150,65 @@ int compute() {
         check(rel_fro(keep(X.to_host()), W) < 1e-5f, "X = f(X) with X on both sides");
     }
 
+    // (11) deferred fills: the constructor's zero-init contract, ones(), partial overwrite, and no launch at all
+    //      for matrices that die (or are replaced) unread
+    {
+        const char* eager = std::getenv("JZ_EAGER");
+        const bool lazy = !(eager && *eager && std::string(eager) != "0");
+        const unsigned long long before = jz_launch_count();
+        {
+            CM W("weights", 64, 48), b("bias", 64, 1), v("val", 64, 32);
+            W = CM::randn(64, 48) * .001;   // the Layer<D> constructor idiom (ml/layer.hpp:67-76)
+            b = CM::randn(64, 1) * .001;
+            v.zeros();
+        }
+        const unsigned long long dead = jz_launch_count() - before;
+        std::cout << "    launches for constructed-and-dropped matrices: " << dead << std::endl;
+        if (lazy) check(dead == 0, "matrices that die unread cost no launch");
+        CM Z("z", 37, 5);
+        Matrix<float> z = keep(Z.to_host());
+        check(max_abs_diff(z, Matrix<float>("z", 37, 5)) == 0.0f, "public constructor is observably zero-filled");
+        CM O = CM::ones(9, 4);
+        O.slice(2, 5, 1, 3, CM(Matrix<float>::randn(3, 2) * 0.0f + 7.0f));   // partial overwrite of a deferred fill
+        Matrix<float> o = keep(O.to_host());
+        bool ok = true;
+        for (size_t j = 0; j < 4; j++)
+            for (size_t i = 0; i < 9; i++) ok &= o.elem(i, j) == ((i >= 2 && i < 5 && j >= 1 && j < 3) ? 7.0f : 1.0f);
+        check(ok, "window assignment into a deferred ones()");
+        CM F2("f", 6, 6);
+        F2.ones();
+        F2 += 2.0f;            // in-place step on a deferred fill
+        CM G = exp(F2 * 0.0f) + F2;   // deferred readers of a deferred fill
+        F2.zeros();            // redefinition after readers were taken
+        check(max_abs_diff(keep(G.to_host()), Matrix<float>::ones(6, 6) * 4.0f) == 0.0f, "readers of a deferred fill see it");
+        check(max_abs_diff(keep(F2.to_host()), Matrix<float>::zeros(6, 6)) == 0.0f, "refill after readers");
+        CM bias = CM::ones(5, 1) * 0.5f, row = CM::ones(1, 7);
+        check(max_abs_diff(keep((bias * row).to_host()), Matrix<float>::ones(5, 7) * 0.5f) == 0.0f, "b * ones(1, N) broadcast");
+    }
+    // (12) deferred draws: values are fixed at creation (counter-based stream), whatever runs or dies in between
+    {
+        GPUSampler s1(11);
+        CM R1 = CM::randn(33, 17);
+        { CM dropped = CM::randn(100, 100); }
+        CM R2 = CM::rand(8, 8);
+        Matrix<float> r2a = R2.to_host(), r1a = R1.to_host();   // materialised in the opposite order
+        GPUSampler s2(11);
+        CM Q1 = CM::randn(33, 17);
+        Matrix<float> q1 = Q1.to_host();
+        CM Qd = CM::randn(100, 100);
+        Matrix<float> qd = Qd.to_host();
+        CM Q2 = CM::rand(8, 8);
+        Matrix<float> q2 = Q2.to_host();
+        check(max_abs_diff(r1a, q1) == 0.0f && max_abs_diff(r2a, q2) == 0.0f, "draws do not depend on evaluation order");
+        double mean = 0, var = 0;
+        for (size_t j = 0; j < 100; j++) for (size_t i = 0; i < 100; i++) mean += qd.elem(i, j);
+        mean /= 1e4;
+        for (size_t j = 0; j < 100; j++) for (size_t i = 0; i < 100; i++) var += (qd.elem(i, j) - mean) * (qd.elem(i, j) - mean);
+        var /= 1e4;
+        check(std::fabs(mean) < 0.05 && std::fabs(var - 1.0) < 0.06, "randn is standard normal");
+        keep(r1a); keep(r2a);
+    }
+
     const std::string path = std::string(PROJECT_DIR) + "/res/test_fusion_dump.bin";
     if (FILE* f = fopen(path.c_str(), "wb")) {
         for (const auto& m : dump) fwrite(m.data(), sizeof(float), m.num_row() * m.num_col(), f);

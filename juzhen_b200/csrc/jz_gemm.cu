@@ -22,10 +22,11 @@
 //     hi/lo images to workspace, 4 TMA loads per stage) is kept for operands TMA cannot
 //     address in place and for A/B measurement (JZ_GEMM_PRESPLIT=1);
 //
-// Fallback path: a bounds-checked fp32 FMA (SIMT) kernel for shapes TMA cannot address
-// (n = 1001 in tests/testEigen.cu, ld = 10 in the MNIST head), for tiny problems and for
-// mode JZ_GEMM_FP32_SIMT; rank-1 products (k == 1: the reference's broadcast idiom) are a
-// streaming outer-product kernel.
+// Other paths: products of at most 2^26 multiply-adds (a training step at batch 32) go to the
+// latency-oriented warp-per-tile fp32 kernel of jz_gemm_small.cu; a bounds-checked shared-memory
+// fp32 FMA (SIMT) kernel takes large shapes the tensor path cannot (m or n < 64) and mode
+// JZ_GEMM_FP32_SIMT; rank-1 products (k == 1: the reference's broadcast idiom) are a streaming
+// outer-product kernel.
 #include <cuda.h>
 
 #include <cstring>
@@ -35,6 +36,12 @@
 #include "jz_math.cuh"
 
 namespace jz {
+
+// jz_gemm_small.cu
+bool gemm_small_wants(size_t m, size_t n, size_t k);
+int launch_gemm_small(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                      const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain,
+                      cudaStream_t s);
 
 // ======================================================================= SIMT fallback
 constexpr int SBM = 64, SBN = 64, SBK = 16;
@@ -981,6 +988,8 @@ static int gemm_local(int ta, int tb, size_t m, size_t n, size_t k, float alpha,
         ctx().gemm_last_path = 3;
         return JZ_OK;
     }
+    if (gemm_small_wants(m, n, k))   // latency-bound sizes: the warp-per-tile fp32 kernel (jz_gemm_small.cu)
+        return launch_gemm_small(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
     const bool want_tc = (mode == JZ_GEMM_3XTF32 || mode == JZ_GEMM_TF32 || mode == JZ_GEMM_BF16) && ctx().cc_major == 10;
     const bool big_enough = m >= 64 && n >= 64 && k >= 32 && (double(m) * double(n) * double(k) >= double(1 << 22));
     const bool fits_i32 = m < (size_t(1) << 31) && n < (size_t(1) << 31) && k < (size_t(1) << 31);

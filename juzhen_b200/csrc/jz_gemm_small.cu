@@ -1,0 +1,209 @@
+// jz_gemm_small.cu -- fp32 FMA GEMM for SMALL products (at most a few 10^7 multiply-adds): the shapes of a
+// training step at batch 32 ((1024 x 784)(784 x 32), (128 x 1024)(1024 x 32), (1024 x 32)(32 x 784),
+// (10 x 128)(128 x 32) ...), replacing cublasSgemm (cpp/cumatrix.cu:177-197) where a tensor-core tile would be
+// mostly padding and its pipeline prologue longer than the product.
+//
+// These products are latency problems, not throughput problems: the whole of A fits in L2 and the math is a few
+// microseconds of one SM row.  A classic shared-memory-tiled kernel serialises global-load latency once per k-tile
+// (measured on B200: 70-90 us for the two forward products above, 57 % of the demo_mnist step).  Here instead:
+//   * a WARP owns 32 rows x NT columns of C for a slice of k, its lanes own the rows: A is read with one
+//     coalesced 128-byte load per k (plain A) or one 128-bit load per lane per 4 k (flagged-transpose A), B with
+//     warp-uniform 128-bit loads served by L1 (4 k per load for plain B, 4 columns per load for flagged B);
+//     no shared memory and no barrier inside the k loop, 4 k in flight per iteration;
+//   * the 8 warps of a CTA either split k eight ways (deep products: partial tiles meet in shared memory once, at
+//     the end, fixed order -> deterministic) or take 8 different column blocks (shallow products, no reduction);
+//   * NT in {8, 16, 32} is chosen so that the grid has at least ~one CTA per SM whenever the shape allows.
+// alpha/beta and the fused elementwise chain are applied exactly as in the other GEMM kernels.
+#include "jz_common.cuh"
+#include "jz_math.cuh"
+
+namespace jz {
+
+constexpr int SK_WARPS = 8;
+
+// op(A)(i, kk .. kk+3) for this lane's row
+template <bool TA, bool VEC>
+__device__ __forceinline__ void sk_load_a(float (&a)[4], const float* __restrict__ A, size_t lda, size_t i, size_t kk) {
+    if constexpr (!TA) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) a[q] = A[(kk + q) * lda + i];
+    } else if constexpr (VEC) {
+        const float4 v = *reinterpret_cast<const float4*>(A + i * lda + kk);
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) a[q] = A[i * lda + kk + q];
+    }
+}
+
+// acc[j] += sum_q a[q] * op(B)(kk + q, j0 + j), j < NT.  Every address is warp-uniform.
+template <bool TB, bool VEC, int NT>
+__device__ __forceinline__ void sk_fma_b(float (&acc)[NT], const float (&a)[4], const float* __restrict__ B, size_t ldb,
+                                         size_t kk, size_t j0, size_t n) {
+    if constexpr (!TB) {   // B(kk, j) at j*ldb + kk: contiguous in k
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            const size_t jj = j0 + j < n ? j0 + j : n - 1;   // clamped: surplus columns are computed, never stored
+            float b[4];
+            if constexpr (VEC) {
+                const float4 v = *reinterpret_cast<const float4*>(B + jj * ldb + kk);
+                b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) b[q] = B[jj * ldb + kk + q];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[j] = fmaf(a[q], b[q], acc[j]);
+        }
+    } else {               // B(kk, j) at kk*ldb + j: contiguous in j
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float* row = B + (kk + q) * ldb;
+#pragma unroll
+            for (int j = 0; j < NT; j += 4) {
+                float b[4];
+                if (VEC && j0 + j + 3 < n) {
+                    const float4 v = *reinterpret_cast<const float4*>(row + j0 + j);
+                    b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; t++) b[t] = row[j0 + j + t < n ? j0 + j + t : n - 1];
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++) acc[j + t] = fmaf(a[q], b[t], acc[j + t]);
+            }
+        }
+    }
+}
+
+// KSPLIT: the CTA's warps split k (true) or take different column blocks (false).
+template <bool TA, bool TB, int NT, bool KSPLIT, bool VEC>
+__global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, size_t n, size_t k, float alpha,
+                                                                   const float* __restrict__ A, size_t lda,
+                                                                   const float* __restrict__ B, size_t ldb, float beta,
+                                                                   float* C, size_t ldc, ChainParams chain_p) {
+    __shared__ ChainParams chain;
+    __shared__ float red[KSPLIT ? SK_WARPS : 1][KSPLIT ? NT : 1][32];
+    stage_chain(&chain, chain_p, threadIdx.x);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t i = size_t(blockIdx.x) * 32 + lane;
+    const size_t il = i < m ? i : m - 1;   // clamped row for loads
+    const size_t j0 = (size_t(blockIdx.y) * (KSPLIT ? 1 : SK_WARPS) + (KSPLIT ? 0 : warp)) * NT;
+    size_t kbeg = 0, kend = k;
+    if (KSPLIT) {
+        const size_t per = ((k + 4 * SK_WARPS - 1) / (4 * SK_WARPS)) * 4;   // multiple of 4: slices keep 16-byte phase
+        kbeg = size_t(warp) * per < k ? size_t(warp) * per : k;
+        kend = kbeg + per < k ? kbeg + per : k;
+    }
+    float acc[NT];
+#pragma unroll
+    for (int j = 0; j < NT; j++) acc[j] = 0.0f;
+    if (KSPLIT || j0 < n) {
+        size_t kk = kbeg;
+        for (; kk + 4 <= kend; kk += 4) {
+            float a[4];
+            sk_load_a<TA, VEC>(a, A, lda, il, kk);
+            sk_fma_b<TB, VEC, NT>(acc, a, B, ldb, kk, j0, n);
+        }
+        for (; kk < kend; kk++) {   // k tail, one at a time
+            const float a = TA ? A[il * lda + kk] : A[kk * lda + il];
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                const size_t jj = j0 + j < n ? j0 + j : n - 1;
+                acc[j] = fmaf(a, TB ? B[kk * ldb + jj] : B[jj * ldb + kk], acc[j]);
+            }
+        }
+    }
+    __syncthreads();   // chain staged (and, below, partial tiles complete)
+    if constexpr (KSPLIT) {
+#pragma unroll
+        for (int j = 0; j < NT; j++) red[warp][j][lane] = acc[j];
+        __syncthreads();
+        // 32 x NT outputs over 256 threads: thread t sums the 8 partials of (row t % 32, columns t / 32 + 8 r)
+#pragma unroll
+        for (int r = 0; r < NT / SK_WARPS; r++) {
+            const int j = warp + SK_WARPS * r;
+            float s = 0.0f;
+#pragma unroll
+            for (int w = 0; w < SK_WARPS; w++) s += red[w][j][lane];
+            if (i < m && j0 + j < n) {
+                float x[1] = {alpha * s};
+                float* dst = C + (j0 + j) * ldc + i;
+                if (beta != 0.0f) x[0] += beta * *dst;
+                if (chain.n) apply_chain<1>(x, chain);
+                *dst = x[0];
+            }
+        }
+    } else {
+        if (i < m) {
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                if (j0 + j < n) {
+                    float x[1] = {alpha * acc[j]};
+                    float* dst = C + (j0 + j) * ldc + i;
+                    if (beta != 0.0f) x[0] += beta * *dst;
+                    if (chain.n) apply_chain<1>(x, chain);
+                    *dst = x[0];
+                }
+            }
+        }
+    }
+}
+
+template <bool TA, bool TB, int NT, bool KSPLIT>
+static int launch_small_v(bool vec, dim3 grid, cudaStream_t s, size_t m, size_t n, size_t k, float alpha, const float* A,
+                          size_t lda, const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain) {
+    if (vec) JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, true>), grid, 32 * SK_WARPS, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    else JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, false>), grid, 32 * SK_WARPS, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    return JZ_OK;
+}
+template <bool TA, bool TB, int NT>
+static int launch_small_k(bool ksplit, bool vec, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                          const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain, cudaStream_t s) {
+    const size_t gx = ceil_div(m, size_t(32));
+    const size_t gy = ceil_div(n, size_t(NT) * (ksplit ? 1 : SK_WARPS));
+    if (gy > 65535) return fail(JZ_ERR_UNSUPPORTED, "small gemm: n too large");
+    const dim3 grid((unsigned)gx, (unsigned)gy, 1);
+    if (ksplit) return launch_small_v<TA, TB, NT, true>(vec, grid, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    return launch_small_v<TA, TB, NT, false>(vec, grid, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+}
+template <bool TA, bool TB>
+static int launch_small_nt(int nt, bool ksplit, bool vec, size_t m, size_t n, size_t k, float alpha, const float* A,
+                           size_t lda, const float* B, size_t ldb, float beta, float* C, size_t ldc,
+                           const ChainParams& chain, cudaStream_t s) {
+    if (nt == 8) return launch_small_k<TA, TB, 8>(ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    if (nt == 16) return launch_small_k<TA, TB, 16>(ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    return launch_small_k<TA, TB, 32>(ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+}
+
+// is this product one for the small kernel?  (m, n, k >= 1 checked by the caller)
+bool gemm_small_wants(size_t m, size_t n, size_t k) {
+    static const bool off = [] { const char* e = std::getenv("JZ_GEMM_NO_SMALL"); return e && e[0] && e[0] != '0'; }();
+    if (off || k < 2) return false;
+    return double(m) * double(n) * double(k) <= double(1 << 26);   // ~2 us of FMA at a third of the SIMT peak
+}
+
+int launch_gemm_small(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                      const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain,
+                      cudaStream_t s) {
+    // 128-bit operand loads need 16-byte phase on the k (or column) runs they cover
+    const bool vec = (!ta || (lda % 4 == 0 && aligned16(A))) && ldb % 4 == 0 && aligned16(B);
+    // deep products split k over the CTA's warps; shallow ones give each warp its own column block
+    const bool ksplit = k >= 256 || n <= 32;
+    const size_t row_blocks = ceil_div(m, size_t(32));
+    const size_t want = size_t(ctx().sm_count) * 4 / 5;
+    int nt = 8;
+    for (int cand : {32, 16, 8}) {
+        nt = cand;
+        if (row_blocks * ceil_div(n, size_t(cand) * (ksplit ? 1 : SK_WARPS)) >= want) break;
+    }
+    int rc;
+    if (!ta && !tb) rc = launch_small_nt<false, false>(nt, ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    else if (ta && !tb) rc = launch_small_nt<true, false>(nt, ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    else if (!ta && tb) rc = launch_small_nt<false, true>(nt, ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    else rc = launch_small_nt<true, true>(nt, ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    if (rc == JZ_OK) ctx().gemm_last_path = 4;
+    return rc;
+}
+
+}  // namespace jz

@@ -283,6 +283,59 @@ int jz_memcpy_h2d(float* dst, const float* src, size_t count, jz_stream_t stream
     return JZ_OK;
 }
 
+// Upload from PAGEABLE host memory without draining the stream.  cudaMemcpyAsync on pageable memory larger than
+// the driver's inline limit makes the host wait until the stream reaches the copy (the driver stages it chunk by
+// chunk at execution time) -- for a training loop that uploads a batch per step (examples/demo_mnist.cu:108-109)
+// that serialises host and device once per step.  Here the host copies into a slot of a pinned ring first (the
+// caller's buffer is free again when this returns, as after a synchronous cudaMemcpy), then the DMA is queued
+// behind whatever the stream is doing.  A slot is reused only after the event recorded behind its DMA completed.
+namespace {
+struct UploadRing {
+    static constexpr int kSlots = 16;
+    static constexpr size_t kSlotBytes = size_t(1) << 19;   // 512 KiB: a 784 x 32 fp32 batch is 98 KiB
+    void* base = nullptr;
+    cudaEvent_t done[kSlots] = {};
+    bool used[kSlots] = {};
+    int next = 0;
+    int device = -1;
+};
+UploadRing g_ring;
+std::mutex g_ring_mu;
+}  // namespace
+
+int jz_upload(float* dst, const float* src, size_t count, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    if (count == 0) return JZ_OK;
+    if (!dst || !src) return fail(JZ_ERR_ARG, "jz_upload: null pointer");
+    const size_t bytes = count * sizeof(float);
+    if (bytes > UploadRing::kSlotBytes) {   // large: the plain path (host waits for the stream, data safe on return)
+        JZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+        return JZ_OK;
+    }
+    std::lock_guard<std::mutex> lock(g_ring_mu);
+    UploadRing& r = g_ring;
+    if (!r.base || r.device != g_ctx.device) {
+        if (r.base) {
+            cudaFreeHost(r.base);
+            for (auto& e : r.done) if (e) { cudaEventDestroy(e); e = nullptr; }
+        }
+        JZ_CUDA(cudaHostAlloc(&r.base, UploadRing::kSlots * UploadRing::kSlotBytes, cudaHostAllocDefault));
+        for (auto& e : r.done) JZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& u : r.used) u = false;
+        r.next = 0;
+        r.device = g_ctx.device;
+    }
+    const int slot = r.next;
+    r.next = (r.next + 1) % UploadRing::kSlots;
+    if (r.used[slot]) JZ_CUDA(cudaEventSynchronize(r.done[slot]));
+    void* stage = static_cast<char*>(r.base) + size_t(slot) * UploadRing::kSlotBytes;
+    std::memcpy(stage, src, bytes);
+    JZ_CUDA(cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    JZ_CUDA(cudaEventRecord(r.done[slot], as_stream(stream)));
+    r.used[slot] = true;
+    return JZ_OK;
+}
+
 int jz_memcpy_d2h(float* dst, const float* src, size_t count, jz_stream_t stream) {
     JZ_INIT_OR_RETURN();
     if (count == 0) return JZ_OK;

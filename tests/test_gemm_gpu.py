@@ -47,7 +47,8 @@ def test_gemm_shape_error(jz):
 
 
 @pytest.mark.parametrize("mode", ["3xtf32", "tf32", "fp32"])
-@pytest.mark.parametrize("shape", [(256, 256, 256), (384, 300, 520), (130, 1000, 70), (1024, 512, 768), (515, 2049, 257)])
+@pytest.mark.parametrize("shape", [(256, 256, 256), (384, 300, 520), (130, 1000, 70), (640, 320, 384), (1024, 512, 768),
+                                   (515, 2049, 257)])
 def test_gemm_all_flags_vs_oracle(jz, port, mode, shape):
     m, k, n = shape
     rng = np.random.default_rng(m * 7 + k * 3 + n)
@@ -61,8 +62,32 @@ def test_gemm_all_flags_vs_oracle(jz, port, mode, shape):
             path = jz.lib().jz_gemm_last_path()
             print(f"gemm {mode} {shape} ta={ta} tb={tb}: rel_fro={err:.3e} path={path}")
             assert err < TOL[mode], (mode, shape, ta, tb, err)
-            if mode != "fp32" and min(m, n) >= 64 and m * n * k >= (1 << 22):
+            if m * n * k <= (1 << 26):
+                assert path == 4, "expected the small-product kernel"
+            elif mode != "fp32" and min(m, n) >= 64:
                 assert path == 1, "expected the tcgen05 kernel"
+
+
+@pytest.mark.parametrize("shape", [(1024, 784, 32), (128, 1024, 32), (10, 128, 32), (1024, 32, 784), (784, 1024, 32),
+                                   (128, 10, 32), (33, 257, 5), (1000, 31, 1000), (2, 4096, 500), (7, 3, 2)])
+def test_gemm_small_products_training_step_shapes(jz, port, shape):
+    """the products of one demo_mnist step at batch 32 and other latency-bound shapes: all four
+    flag combinations, ragged edges, leading dimensions that defeat 128-bit loads, alpha/beta"""
+    m, k, n = shape
+    rng = np.random.default_rng(m + 3 * k + 7 * n)
+    P, Q = F(rng.standard_normal((m, k))), F(rng.standard_normal((k, n)))
+    truth = port.gemm(P, 0, Q, 0, f64=True)
+    L = jz.lib()
+    for ta in (0, 1):
+        for tb in (0, 1):
+            a, b = operands(jz, P, Q, ta, tb)
+            got = a.dot(b, mode=0).to_host()
+            assert L.jz_gemm_last_path() == 4
+            assert rel_fro(got, truth) < 1e-5, (shape, ta, tb)
+    C0 = F(rng.standard_normal((m, n)))
+    a, b, c = jz.CM(P), jz.CM(Q), jz.CM(C0)
+    jz._lib.check(L.jz_gemm(0, 0, m, n, k, 0.75, a.ptr, m, b.ptr, k, -0.5, c.ptr, m, 0, None))
+    assert rel_fro(c.to_host(), 0.75 * truth.astype(np.float64) - 0.5 * C0) < 1e-5
 
 
 def test_gemm_tf32_is_actually_tf32_and_3x_is_fp32_grade(jz, port):
