@@ -154,10 +154,12 @@ void Storage::flush_readers() {
 void Storage::before_write() {
     flush_readers();
     materialize();
+    konst_known = false;
 }
 
 void Storage::append(const jz_step& s) {
     flush_readers();  // they were defined on the value before this step
+    konst_known = false;
     if (!lazy_ok()) {
         materialize();
         run_program(ptr, ptr, count, std::vector<jz_step>{s});
@@ -171,6 +173,8 @@ void Storage::define(std::unique_ptr<Producer> p) {
     flush_readers();   // deferred readers were defined on the old value
     pending.clear();   // ... which nobody else can ask for any more
     producer.reset();
+    konst_known = p->kind == Producer::FILL;
+    konst = p->value;
     if (lazy_ok()) {
         producer = std::move(p);
         return;
@@ -367,9 +371,55 @@ Matrix<CUDAfloat> Matrix<CUDAfloat>::add(const Matrix<CUDAfloat>& B, float s1, f
     return C;
 }
 
+// The reference spells "add a column (row) vector to every column (row)" as a rank-1 GEMM against a vector of
+// ones followed by a full add: W*x + b*ones(1,N) (ml/layer.hpp:79,120), input - oneK1*mx (ml/layer.hpp:260),
+// m = ones(n,1)*mean (cpp/juzhen.hpp:88-104).  When one side of an in-place add is such a product that has not
+// been computed yet, the ones vector, the m x n outer product and the separate add collapse into ONE broadcast
+// pass.  Bit-identical to the unfused order: u[i]*1.0f is exact, and the pass applies the same
+// separately rounded s1*x + s2*y.
+//   returns the storage of the vector and dim (1: out(i,j) gets vec[i]; 0: vec[j]) if `st` is a deferred u*1^T / 1*v^T
+static StoragePtr deferred_broadcast(const jzb200::Storage& st, size_t rows, size_t cols, int& dim) {
+    const Producer* g = st.producer.get();
+    if (!g || g->kind != Producer::GEMM || g->k != 1 || !st.pending.empty() || g->m != rows || g->n != cols) return nullptr;
+    const size_t su = g->ta ? g->lda : 1, sv = g->tb ? 1 : g->ldb;   // element strides of u = op(A)(:,0), v = op(B)(0,:)
+    auto is_one = [](const StoragePtr& s) { return s->konst_known && s->konst == 1.0f && s->pending.empty(); };
+    if (is_one(g->b) && (su == 1 || rows == 1)) { dim = 1; return g->a; }
+    if (is_one(g->a) && (sv == 1 || cols == 1)) { dim = 0; return g->b; }
+    return nullptr;
+}
+
+bool Matrix<CUDAfloat>::add_broadcast(const Matrix<CUDAfloat>& B, float s1, float s2) {
+    if (transpose || B.transpose || !jzb200::lazy_enabled() || count() == 0) return false;
+    const StoragePtr mine = elements.storage(), theirs = B.elements.storage();
+    if (mine == theirs) return false;
+    int dim = 0;
+    // this = s1*this + s2*(u 1^T): one pass over this
+    if (const Producer* g = theirs->producer.get(); g && g->a != mine && g->b != mine) {
+        if (StoragePtr vec = deferred_broadcast(*theirs, numrow, numcol, dim)) {
+            vec->materialize();
+            float* x = wdev();
+            JZ_DO(jz_add_bcast(x, x, numrow, numcol, vec->ptr, dim, s1, s2, S()));
+            return true;
+        }
+    }
+    // this = s1*(u 1^T) + s2*B, this being the not-yet-computed product: one pass from B into this buffer
+    if (StoragePtr vec = deferred_broadcast(*mine, numrow, numcol, dim)) {
+        if (vec == theirs || !mine->lazy_ok()) return false;
+        const float* b = B.dev();
+        mine->flush_readers();
+        if (!mine->producer) return false;   // a deferred reader needed the product itself after all
+        vec->materialize();
+        mine->producer.reset();
+        JZ_DO(jz_add_bcast(mine->ptr, b, numrow, numcol, vec->ptr, dim, s2, s1, S()));
+        return true;
+    }
+    return false;
+}
+
 // in place: the result keeps this layout, B is read transposed iff the flags differ (cpp/cumatrix.cu:246-260)
 void Matrix<CUDAfloat>::add(const Matrix<CUDAfloat>& B, float s1, float s2) {
     require_same_shape(*this, B);
+    if (add_broadcast(B, s1, s2)) return;
     const float* b = B.dev();  // before wdev(): B may be a deferred view of this very storage
     float* x = wdev();
     if (transpose == B.transpose) JZ_DO(jz_axpby(x, x, b, count(), s1, s2, S()));

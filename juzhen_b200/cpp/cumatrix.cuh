@@ -100,6 +100,8 @@ class Matrix<CUDAfloat> {
         return store().ptr;
     }
     size_t count() const { return numrow * numcol; }
+    // in-place add against a not-yet-computed u*ones^T / ones*v^T product as one broadcast pass (cumatrix.cu)
+    bool add_broadcast(const Matrix<CUDAfloat>& B, float s1, float s2);
     // deferred out-of-place elementwise result (same physical shape and flag as this matrix)
     Matrix<CUDAfloat> mapped(const char* name, const jz_step& step) const;
 

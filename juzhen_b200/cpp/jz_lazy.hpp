@@ -51,6 +51,8 @@ struct Storage {
     float* ptr = nullptr;
     size_t count = 0;
     bool escaped = false;                         // raw pointer handed out by data()
+    bool konst_known = false;                     // every element is known to equal `konst` (set by fills, cleared
+    float konst = 0.0f;                           // by anything that may change the bytes)
     std::vector<jz_step> pending;                 // deferred in-place program
     std::unique_ptr<Producer> producer;           // deferred definition of the contents
     std::vector<std::weak_ptr<Storage>> readers;  // storages whose producer reads this one

@@ -209,6 +209,51 @@ int compute() {
         keep(r1a); keep(r2a);
     }
 
+    // (13) the broadcast idioms (rank-1 product against ones + full add) as one pass, bit-identical to the CPU path
+    {
+        const char* eager = std::getenv("JZ_EAGER");
+        const bool lazy = !(eager && *eager && std::string(eager) != "0");
+        auto W = Matrix<float>::randn(64, 48), X = Matrix<float>::randn(48, 32), b = Matrix<float>::randn(64, 1);
+        auto mx = Matrix<float>::randn(1, 32), v = Matrix<float>::randn(1, 32);
+        CM dW(W), dX(X), db(b), dmx(mx), dv(v);
+        jz_sync(nullptr);
+        unsigned long long before = jz_launch_count();
+        CM H = tanh(dW * dX + db * CM::ones(1, 32));                 // Layer<D>::eval, ml/layer.hpp:118-121
+        Matrix<float> h = keep(H.to_host());
+        unsigned long long launches = jz_launch_count() - before;
+        std::cout << "    tanh(W*x + b*ones) launches: " << launches << std::endl;
+        if (lazy) check(launches <= 3, "layer forward: GEMM + broadcast add + tanh (<= 3 launches)");
+        Matrix<float> wantH = tanh(W * X + b * Matrix<float>::ones(1, 32));
+        std::cout << "    max |diff| vs CPU: " << max_abs_diff(h, wantH) << std::endl;
+        check(max_abs_diff(h, wantH) < 2e-5f, "tanh(W*x + b*ones(1,N)) matches the CPU path (different fp32 summation order)");
+        {   // and bit-identical to the unfused order on the same device product
+            CM P0 = dW * dX;
+            Matrix<float> p0 = P0.to_host();
+            check(max_abs_diff(h, tanh(p0 + b * Matrix<float>::ones(1, 32))) < 5e-7f, "broadcast add equals product + b*ones on the device product");
+        }
+        CM P = dW * dX;
+        Matrix<float> Ph = P.to_host();
+        CM one_k1("oneK1", 64, 1);
+        one_k1.ones();
+        before = jz_launch_count();
+        CM S1 = P - one_k1 * dmx;                                     // LogisticLayer::grad, ml/layer.hpp:260
+        Matrix<float> s1h = keep(S1.to_host());
+        launches = jz_launch_count() - before;
+        std::cout << "    X - ones*mx launches: " << launches << std::endl;
+        if (lazy) check(launches <= 2, "column-max subtraction: ones fill (first use) + one broadcast pass");
+        check(max_abs_diff(s1h, Ph - Matrix<float>::ones(64, 1) * mx) == 0.0f, "X - oneK1*mx is bit-identical to the CPU path");
+        CM S2 = P - one_k1 * dmx;                                     // second use: oneK1 is real bytes now, still known to be ones
+        check(max_abs_diff(keep(S2.to_host()), s1h) == 0.0f, "same with a materialised ones vector");
+        one_k1 += 1.0f;                                               // no longer ones: must take the general path
+        CM S3 = P - one_k1 * dmx;
+        check(max_abs_diff(keep(S3.to_host()), Ph - (Matrix<float>::ones(64, 1) * 2.0f) * mx) < 1e-5f, "modified vector is not mistaken for ones");
+        CM S4 = P + db * dv;                                          // genuine rank-1 update
+        check(max_abs_diff(keep(S4.to_host()), Ph + b * v) < 1e-5f, "general rank-1 product still exact");
+        CM Pt = (dX.T() * dW.T());                                    // (W*X)^T materialised non-transposed: 32 x 64
+        CM S5 = Pt.T() + db * CM::ones(1, 32);                        // flagged operand: falls back to the transposing add
+        check(max_abs_diff(keep(S5.to_host()), Ph + b * Matrix<float>::ones(1, 32)) < 1e-5f, "flagged operand takes the general path");
+    }
+
     const std::string path = std::string(PROJECT_DIR) + "/res/test_fusion_dump.bin";
     if (FILE* f = fopen(path.c_str(), "wb")) {
         for (const auto& m : dump) fwrite(m.data(), sizeof(float), m.num_row() * m.num_col(), f);

@@ -22,10 +22,10 @@
 //     hi/lo images to workspace, 4 TMA loads per stage) is kept for operands TMA cannot
 //     address in place and for A/B measurement (JZ_GEMM_PRESPLIT=1);
 //
-// Other paths: products of at most 2^26 multiply-adds (a training step at batch 32) go to the
-// latency-oriented warp-per-tile fp32 kernel of jz_gemm_small.cu; a bounds-checked shared-memory
-// fp32 FMA (SIMT) kernel takes large shapes the tensor path cannot (m or n < 64) and mode
-// JZ_GEMM_FP32_SIMT; rank-1 products (k == 1: the reference's broadcast idiom) are a streaming
+// Other paths: shapes the tensor path does not take (m or n < 64, k < 32, tiny, or operands it cannot
+// address) go to the latency-oriented warp-per-tile fp32 kernel of jz_gemm_small.cu when the product
+// is at most 2^26 multiply-adds (a training step at batch 32), else to a bounds-checked
+// shared-memory fp32 FMA (SIMT) kernel, which also serves mode JZ_GEMM_FP32_SIMT; rank-1 products (k == 1: the reference's broadcast idiom) are a streaming
 // outer-product kernel.
 #include <cuda.h>
 
@@ -988,8 +988,6 @@ static int gemm_local(int ta, int tb, size_t m, size_t n, size_t k, float alpha,
         ctx().gemm_last_path = 3;
         return JZ_OK;
     }
-    if (gemm_small_wants(m, n, k))   // latency-bound sizes: the warp-per-tile fp32 kernel (jz_gemm_small.cu)
-        return launch_gemm_small(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
     const bool want_tc = (mode == JZ_GEMM_3XTF32 || mode == JZ_GEMM_TF32 || mode == JZ_GEMM_BF16) && ctx().cc_major == 10;
     const bool big_enough = m >= 64 && n >= 64 && k >= 32 && (double(m) * double(n) * double(k) >= double(1 << 22));
     const bool fits_i32 = m < (size_t(1) << 31) && n < (size_t(1) << 31) && k < (size_t(1) << 31);
@@ -1000,6 +998,8 @@ static int gemm_local(int ta, int tb, size_t m, size_t n, size_t k, float alpha,
         *peers_done = true;
         return tc::gemm_tc(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, split, chain, peers, n_peers, s);
     }
+    if (gemm_small_wants(m, n, k))   // latency-bound shapes: the warp-per-tile fp32 kernel (jz_gemm_small.cu)
+        return launch_gemm_small(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
     return launch_simt(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
 }
 

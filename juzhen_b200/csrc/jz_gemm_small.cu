@@ -6,20 +6,24 @@
 // These products are latency problems, not throughput problems: the whole of A fits in L2 and the math is a few
 // microseconds of one SM row.  A classic shared-memory-tiled kernel serialises global-load latency once per k-tile
 // (measured on B200: 70-90 us for the two forward products above, 57 % of the demo_mnist step).  Here instead:
-//   * a WARP owns 32 rows x NT columns of C for a slice of k, its lanes own the rows: A is read with one
+//   * a WARP owns 32 rows x 8 columns of C for a slice of k, its lanes own the rows: A is read with one
 //     coalesced 128-byte load per k (plain A) or one 128-bit load per lane per 4 k (flagged-transpose A), B with
 //     warp-uniform 128-bit loads served by L1 (4 k per load for plain B, 4 columns per load for flagged B);
-//     no shared memory and no barrier inside the k loop, 4 k in flight per iteration;
-//   * the 8 warps of a CTA either split k eight ways (deep products: partial tiles meet in shared memory once, at
-//     the end, fixed order -> deterministic) or take 8 different column blocks (shallow products, no reduction);
-//   * NT in {8, 16, 32} is chosen so that the grid has at least ~one CTA per SM whenever the shape allows.
+//     no shared memory and no barrier inside the k loop;
+//   * the 8 / 16 / 32 warps of a CTA split k (every iteration of a warp is one memory round trip, so deep
+//     products want many short slices); the partial tiles meet in shared memory once, at the end, and are
+//     summed in a fixed order -> deterministic results;
+//   * narrow column blocks keep the grid at >= one CTA per SM for the shapes that matter; A is re-read from L2
+//     by the CTAs that share a row block.
+// Measured on B200 inside a launch loop (scripts/small_gemm_bench.py, warm L2): (1024 x 784)(784 x 32) 51 -> 10 us,
+// (128 x 1024)(1024 x 32) 71 -> 12 us, (1024 x 784)^T(1024 x 32) 72 -> 16 us against the shared-memory-tiled kernel.
+// Products with m, n >= 64 and k >= 32 stay on the tensor-core path (8 us at (1024 x 32)(32 x 784)).
 // alpha/beta and the fused elementwise chain are applied exactly as in the other GEMM kernels.
 #include "jz_common.cuh"
 #include "jz_math.cuh"
 
 namespace jz {
 
-constexpr int SK_WARPS = 8;
 
 // op(A)(i, kk .. kk+3) for this lane's row
 template <bool TA, bool VEC>
@@ -77,7 +81,7 @@ __device__ __forceinline__ void sk_fma_b(float (&acc)[NT], const float (&a)[4], 
 }
 
 // KSPLIT: the CTA's warps split k (true) or take different column blocks (false).
-template <bool TA, bool TB, int NT, bool KSPLIT, bool VEC>
+template <bool TA, bool TB, int NT, bool KSPLIT, bool VEC, int SK_WARPS>
 __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, size_t n, size_t k, float alpha,
                                                                    const float* __restrict__ A, size_t lda,
                                                                    const float* __restrict__ B, size_t ldb, float beta,
@@ -100,6 +104,7 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
     for (int j = 0; j < NT; j++) acc[j] = 0.0f;
     if (KSPLIT || j0 < n) {
         size_t kk = kbeg;
+#pragma unroll 2
         for (; kk + 4 <= kend; kk += 4) {
             float a[4];
             sk_load_a<TA, VEC>(a, A, lda, il, kk);
@@ -119,10 +124,11 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
 #pragma unroll
         for (int j = 0; j < NT; j++) red[warp][j][lane] = acc[j];
         __syncthreads();
-        // 32 x NT outputs over 256 threads: thread t sums the 8 partials of (row t % 32, columns t / 32 + 8 r)
+        // 32 x NT outputs: warp w sums the partials of columns w, w + SK_WARPS, ... (lane = row), fixed order
 #pragma unroll
-        for (int r = 0; r < NT / SK_WARPS; r++) {
+        for (int r = 0; r < (NT + SK_WARPS - 1) / SK_WARPS; r++) {
             const int j = warp + SK_WARPS * r;
+            if (j >= NT) break;
             float s = 0.0f;
 #pragma unroll
             for (int w = 0; w < SK_WARPS; w++) s += red[w][j][lane];
@@ -150,37 +156,40 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
     }
 }
 
-template <bool TA, bool TB, int NT, bool KSPLIT>
-static int launch_small_v(bool vec, dim3 grid, cudaStream_t s, size_t m, size_t n, size_t k, float alpha, const float* A,
-                          size_t lda, const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain) {
-    if (vec) JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, true>), grid, 32 * SK_WARPS, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
-    else JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, false>), grid, 32 * SK_WARPS, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
-    return JZ_OK;
-}
-template <bool TA, bool TB, int NT>
-static int launch_small_k(bool ksplit, bool vec, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
-                          const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain, cudaStream_t s) {
+template <bool TA, bool TB, int NT, bool KSPLIT, int W>
+static int launch_small_v(bool vec, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda, const float* B,
+                          size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain, cudaStream_t s) {
     const size_t gx = ceil_div(m, size_t(32));
-    const size_t gy = ceil_div(n, size_t(NT) * (ksplit ? 1 : SK_WARPS));
+    const size_t gy = ceil_div(n, size_t(NT) * (KSPLIT ? 1 : W));
     if (gy > 65535) return fail(JZ_ERR_UNSUPPORTED, "small gemm: n too large");
     const dim3 grid((unsigned)gx, (unsigned)gy, 1);
-    if (ksplit) return launch_small_v<TA, TB, NT, true>(vec, grid, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
-    return launch_small_v<TA, TB, NT, false>(vec, grid, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    if (vec) JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, true, W>), grid, 32 * W, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    else JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, false, W>), grid, 32 * W, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    return JZ_OK;
 }
+// variants: k split over 8 / 16 / 32 warps, 8-column blocks
 template <bool TA, bool TB>
-static int launch_small_nt(int nt, bool ksplit, bool vec, size_t m, size_t n, size_t k, float alpha, const float* A,
-                           size_t lda, const float* B, size_t ldb, float beta, float* C, size_t ldc,
-                           const ChainParams& chain, cudaStream_t s) {
-    if (nt == 8) return launch_small_k<TA, TB, 8>(ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
-    if (nt == 16) return launch_small_k<TA, TB, 16>(ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
-    return launch_small_k<TA, TB, 32>(ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+static int launch_small_cfg(bool ksplit, int warps, int nt, bool vec, size_t m, size_t n, size_t k, float alpha,
+                            const float* A, size_t lda, const float* B, size_t ldb, float beta, float* C, size_t ldc,
+                            const ChainParams& chain, cudaStream_t s) {
+#define JZ_SMALL_CASE(KS, W, NT_) \
+    if (ksplit == KS && warps == W && nt == NT_) \
+        return launch_small_v<TA, TB, NT_, KS, W>(vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    JZ_SMALL_CASE(true, 8, 8) JZ_SMALL_CASE(true, 16, 8) JZ_SMALL_CASE(true, 32, 8)
+#undef JZ_SMALL_CASE
+    return fail(JZ_ERR_ARG, "small gemm: no kernel variant for ksplit=%d warps=%d nt=%d", int(ksplit), warps, nt);
 }
 
 // is this product one for the small kernel?  (m, n, k >= 1 checked by the caller)
 bool gemm_small_wants(size_t m, size_t n, size_t k) {
     static const bool off = [] { const char* e = std::getenv("JZ_GEMM_NO_SMALL"); return e && e[0] && e[0] != '0'; }();
     if (off || k < 2) return false;
-    return double(m) * double(n) * double(k) <= double(1 << 26);   // ~2 us of FMA at a third of the SIMT peak
+    return double(m) * double(n) * double(k) <= double(1 << 26);
+}
+
+static int env_int(const char* name) {
+    const char* e = std::getenv(name);
+    return e && *e ? std::atoi(e) : -1;
 }
 
 int launch_gemm_small(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
@@ -188,20 +197,17 @@ int launch_gemm_small(int ta, int tb, size_t m, size_t n, size_t k, float alpha,
                       cudaStream_t s) {
     // 128-bit operand loads need 16-byte phase on the k (or column) runs they cover
     const bool vec = (!ta || (lda % 4 == 0 && aligned16(A))) && ldb % 4 == 0 && aligned16(B);
-    // deep products split k over the CTA's warps; shallow ones give each warp its own column block
-    const bool ksplit = k >= 256 || n <= 32;
-    const size_t row_blocks = ceil_div(m, size_t(32));
-    const size_t want = size_t(ctx().sm_count) * 4 / 5;
-    int nt = 8;
-    for (int cand : {32, 16, 8}) {
-        nt = cand;
-        if (row_blocks * ceil_div(n, size_t(cand) * (ksplit ? 1 : SK_WARPS)) >= want) break;
-    }
+    static const int f_warps = env_int("JZ_SMALL_WARPS");
+    const bool ksplit = true;
+    const int nt = 8;
+    // more warps = shorter serial k per warp (measured: k = 784: 16.4 / 14.4 / 10.3 us with 8 / 16 / 32 warps)
+    int warps = k >= 512 ? 32 : (k >= 128 ? 16 : 8);
+    if (f_warps == 8 || f_warps == 16 || f_warps == 32) warps = f_warps;
     int rc;
-    if (!ta && !tb) rc = launch_small_nt<false, false>(nt, ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
-    else if (ta && !tb) rc = launch_small_nt<true, false>(nt, ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
-    else if (!ta && tb) rc = launch_small_nt<false, true>(nt, ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
-    else rc = launch_small_nt<true, true>(nt, ksplit, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    if (!ta && !tb) rc = launch_small_cfg<false, false>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    else if (ta && !tb) rc = launch_small_cfg<true, false>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    else if (!ta && tb) rc = launch_small_cfg<false, true>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    else rc = launch_small_cfg<true, true>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
     if (rc == JZ_OK) ctx().gemm_last_path = 4;
     return rc;
 }
