@@ -307,6 +307,12 @@ def run_ours(args):
     cpu = None
     if rank == 0 and not args.no_cpu:
         cpu = cpu_reference_subprocess(log2n=args.cpu_log2n, steps=1)
+    mnist = None
+    if rank == 0 and world == 1 and not args.no_mnist:
+        try:
+            mnist = mnist_step_block()
+        except Exception as e:  # noqa: BLE001 - informative block only
+            mnist = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         line = {
@@ -318,7 +324,7 @@ def run_ours(args):
                        "l2": "inputs (1 GiB/operand) larger than L2, no flush", "ops": [n for n, _ in SWEEP],
                        "algorithmic_bytes_per_step": sw.bytes_per_step, "parallelism": f"independent shards x{world}"},
             "frac_of_hbm_peak": round(value / world / pk["hbm_gbs"], 3),
-            "roofline": roofline, "ops": per_op, "gemm": gemm, "sharded_gemm": sharded, "e2e": e2e,
+            "roofline": roofline, "ops": per_op, "gemm": gemm, "sharded_gemm": sharded, "mnist_step": mnist, "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk, "cpu_baseline": cpu,
         }
@@ -366,6 +372,56 @@ def run_sharded_gemm(jz, L, args, world, rank, stream, timed, pk):
         out[str(n)] = res
         del a, b
     return out
+
+
+# ---------------------------------------------------------------------------------- config 4 (launch-bound)
+def mnist_step_block():
+    """BASELINE configs[3]: one demo_mnist training step (784-1024-128-10 MLP, batch 32, Adam) -- the reference's own
+    program, unchanged, built against this backend (build/dropin/bin/demo_mnist) and against the reference's CUDA
+    sources + cuBLAS (oracle/_ref/cuda/demo_mnist), both run here on the same GPU.  Wall-clock between the
+    program's own progress lines (one every 1000 steps); launch-bound, so no roofline fraction."""
+    ours = os.path.join(ROOT, "build", "dropin", "bin", "demo_mnist")
+    ref = os.path.join(ROOT, "oracle", "_ref", "cuda", "demo_mnist")
+    proj = os.path.join(ROOT, "build", "dropin", "project")
+    if not os.path.exists(ours):
+        return None
+    subprocess.run([sys.executable, os.path.join(ROOT, "juzhen_b200", "cpp", "build_dropin.py"), "--extract-datasets"],
+                   capture_output=True, timeout=300)
+
+    def per_1000(binary, env_extra):
+        env = dict(os.environ, **env_extra)
+        try:
+            p = subprocess.Popen([binary], cwd=proj, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        except OSError as e:
+            return {"error": str(e)}
+        stamps, launches = [], None
+        t_end = time.time() + 180
+        for ln in p.stdout:
+            if "Misclassification Rate" in ln:
+                stamps.append(time.perf_counter())
+            if "jz_stats" in ln and "kernel launches" in ln:
+                launches = int(ln.split("ms,")[1].split("kernel")[0])
+            if time.time() > t_end:
+                p.kill()
+                break
+        p.wait()
+        gaps = sorted(b - a for a, b in zip(stamps, stamps[1:]))
+        if not gaps:
+            return {"error": "no progress lines"}
+        out = {"ms_per_step": round(gaps[len(gaps) // 2], 4), "intervals": len(gaps)}   # median s per 1000 steps = ms per step
+        if launches:
+            out["launches_per_step"] = round(launches / 10000.0, 1)
+        return out
+
+    blk = {"workload": "examples/demo_mnist.cu unchanged: 10000 Adam steps, batch 32, test pass every 1000 steps (inside the interval)",
+           "ours": per_1000(ours, {"JZ_STATS": "1"})}
+    if os.path.exists(ref):
+        blk["reference_cuda_cublas"] = per_1000(ref, {})
+        try:
+            blk["speedup_vs_reference_cuda"] = round(blk["reference_cuda_cublas"]["ms_per_step"] / blk["ours"]["ms_per_step"], 2)
+        except (KeyError, ZeroDivisionError):
+            pass
+    return blk
 
 
 # ---------------------------------------------------------------------------------- reference arm (CPU)
@@ -468,6 +524,7 @@ def main():
     ap.add_argument("--sharded-n", type=int, nargs="*", default=[16384, 32768], dest="sharded_n")
     ap.add_argument("--no-gemm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-mnist", action="store_true", dest="no_mnist")
     ap.add_argument("--_cpu_child", action="store_true")
     args = ap.parse_args()
     if args._cpu_child:
