@@ -18,11 +18,21 @@
 //                      deterministic for a given shape.
 //  dim 1 (reduce across columns, i.e. add the columns into a vector):
 //    each thread owns 4 consecutive rows (float4) and walks columns; the columns are split
-//    across threadIdx.y and across CTAs (grid.y); CTAs write per-chunk partial vectors which
-//    a second pass folds.  Every global read is a full coalesced row segment.
+//    across threadIdx.y and across CTAs (grid.y).  Every global read is a full coalesced row
+//    segment.  The column chunks meet in ONE launch: the 8 CTAs of a thread-block cluster
+//    (cluster dims 1 x 8) add their partial vectors through distributed shared memory, each
+//    cluster writes one partial vector, and the last CTA of a row block to finish (a ticket
+//    counter after __threadfence) folds the few cluster partials in fixed order -- no float
+//    atomics, deterministic per shape, no second kernel (which cost 7 us: 40 % of a 4096^2
+//    row sum).  Shapes with fewer than 8 column chunks keep the plain two-pass form.
+#include <cooperative_groups.h>
+
 #include <cfloat>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 #include <type_traits>
+#include <unordered_map>
 
 #include "jz_common.cuh"
 #include "jz_math.cuh"
@@ -203,9 +213,14 @@ __global__ void __launch_bounds__(256) colreduce_chunk_kernel(float* partial, co
 
 // ------------------------------------------------------------------ dim 1 (across columns)
 // block (tx, ty); thread owns VEC rows; columns [j_begin, j_end) of this CTA's chunk are strided over ty.
-template <class Op, int VEC>
-__global__ void __launch_bounds__(256) rowreduce_kernel(float* out /* nchunks x rows */, const float* a, size_t rows,
-                                                        size_t cols, size_t ld, size_t cols_per_chunk) {
+constexpr int kRowCluster = 8;   // CTAs per cluster along the column-chunk axis (portable maximum)
+
+// CLUSTER = false: writes one partial vector per column chunk (out: nchunks x rows).
+// CLUSTER = true : gridDim.y is a multiple of kRowCluster; out: (nchunks / kRowCluster) x rows partial vectors, and the
+//                  last CTA of each row block folds them into `final_out` (see the file header).
+template <class Op, int VEC, bool CLUSTER>
+__global__ void __launch_bounds__(256) rowreduce_kernel(float* out, const float* a, size_t rows, size_t cols, size_t ld,
+                                                        size_t cols_per_chunk, float* final_out, unsigned* tickets) {
     extern __shared__ float sm[];  // ty x (tx*VEC)
     const size_t row_units = rows / VEC;
     const size_t iu = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -255,11 +270,61 @@ __global__ void __launch_bounds__(256) rowreduce_kernel(float* out /* nchunks x 
 #pragma unroll
     for (int q = 0; q < VEC; q++) sm[threadIdx.y * width + threadIdx.x * VEC + q] = acc[q];
     __syncthreads();
-    for (int e = threadIdx.y * blockDim.x + threadIdx.x; e < width; e += blockDim.x * blockDim.y) {
-        float t = Op::init();
-        for (int yy = 0; yy < int(blockDim.y); yy++) t = Op::apply(t, sm[yy * width + e]);
-        const size_t row = size_t(blockIdx.x) * width + e;
-        if (row < rows) out[size_t(blockIdx.y) * rows + row] = t;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
+    if constexpr (!CLUSTER) {
+        for (int e = tid; e < width; e += nthreads) {
+            float t = Op::init();
+            for (int yy = 0; yy < int(blockDim.y); yy++) t = Op::apply(t, sm[yy * width + e]);
+            const size_t row = size_t(blockIdx.x) * width + e;
+            if (row < rows) out[size_t(blockIdx.y) * rows + row] = t;
+        }
+    } else {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        // this CTA's vector, folded over threadIdx.y, left in sm[0 .. width) (column e is touched by one thread only)
+        for (int e = tid; e < width; e += nthreads) {
+            float t = Op::init();
+            for (int yy = 0; yy < int(blockDim.y); yy++) t = Op::apply(t, sm[yy * width + e]);
+            sm[e] = t;
+        }
+        cluster.sync();
+        // CTA r of the cluster adds slice r of the 8 vectors through distributed shared memory, fixed order
+        const unsigned r = cluster.block_rank();
+        const int per = (width + kRowCluster - 1) / kRowCluster;
+        const size_t cchunk = blockIdx.y / kRowCluster;
+        for (int e = int(r) * per + tid; e < int(r + 1) * per && e < width; e += nthreads) {
+            float t = Op::init();
+#pragma unroll
+            for (int q = 0; q < kRowCluster; q++) t = Op::apply(t, cluster.map_shared_rank(sm, q)[e]);
+            const size_t row = size_t(blockIdx.x) * width + e;
+            if (row < rows) out[cchunk * rows + row] = t;
+        }
+        cluster.sync();   // nobody exits while its shared memory may still be read
+        // ticket: the last CTA of this row block folds the cluster partials
+        __shared__ bool last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last = atomicAdd(&tickets[blockIdx.x], 1u) == gridDim.y - 1;
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            const size_t nclusters = gridDim.y / kRowCluster;
+            for (int e = tid; e < width; e += nthreads) {
+                const size_t row = size_t(blockIdx.x) * width + e;
+                if (row >= rows) continue;
+                float t0 = Op::init(), t1 = t0, t2 = t0, t3 = t0;
+                size_t c = 0;
+                for (; c + 4 <= nclusters; c += 4) {
+                    t0 = Op::apply(t0, __ldcg(out + c * rows + row));
+                    t1 = Op::apply(t1, __ldcg(out + (c + 1) * rows + row));
+                    t2 = Op::apply(t2, __ldcg(out + (c + 2) * rows + row));
+                    t3 = Op::apply(t3, __ldcg(out + (c + 3) * rows + row));
+                }
+                for (; c < nclusters; c++) t0 = Op::apply(t0, __ldcg(out + c * rows + row));
+                final_out[row] = Op::apply(Op::apply(t0, t1), Op::apply(t2, t3));
+            }
+            if (tid == 0) tickets[blockIdx.x] = 0;   // ready for the next launch on this stream
+        }
     }
 }
 
@@ -426,6 +491,24 @@ __global__ void nrm2_final_kernel(float* out, const double* partial, int n) {
 }
 
 // ------------------------------------------------------------------ host dispatch
+// Zero-initialised ticket counters, one block per stream (kernels on a stream are serialised, and each launch
+// leaves its counters at zero again, so a block is never shared by two running kernels).
+constexpr size_t kTicketSlots = 4096;
+static unsigned* tickets_for(cudaStream_t s) {
+    static std::mutex mu;
+    static std::unordered_map<unsigned long long, unsigned*> blocks;   // key: (device, stream)
+    std::lock_guard<std::mutex> lock(mu);
+    const unsigned long long key = (unsigned long long)reinterpret_cast<uintptr_t>(s) * 64ull + (unsigned long long)(ctx().device & 63);
+    auto it = blocks.find(key);
+    if (it != blocks.end()) return it->second;
+    unsigned* p = nullptr;
+    if (cudaMalloc(&p, kTicketSlots * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // zeroed on the SAME stream: ordered before the first kernel that uses it, whatever kind of stream s is
+    if (cudaMemsetAsync(p, 0, kTicketSlots * sizeof(unsigned), s) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
+    blocks[key] = p;
+    return p;
+}
+
 template <class Op>
 static int reduce_dim1(float* out, const float* a, size_t rows, size_t cols, size_t ld, cudaStream_t s);
 
@@ -438,12 +521,16 @@ static size_t stream_cap() {
     }();
     return v;
 }
-static size_t row_waves() {
-    static const size_t v = [] {
+// CTAs per SM-slot for the dim-1 column split.  Measured on B200 (profiles/r01w_rowreduce_tuning.log): one wave is
+// best up to 2^26 elements (fewer, longer chunks: 0.68 / 0.83 of the copy peak at 2^24 / 2^26 against 0.51 / 0.72
+// with two), two waves at 2^28 (0.97 against 0.93).  JZ_REDUCE_WAVES overrides.
+static size_t row_waves(size_t elems) {
+    static const size_t forced = [] {
         const char* e = std::getenv("JZ_REDUCE_WAVES");
-        return e ? size_t(std::atoll(e)) : size_t(2);
+        return e ? size_t(std::atoll(e)) : size_t(0);
     }();
-    return v;
+    if (forced) return forced;
+    return elems >= (size_t(1) << 27) ? 2 : 1;
 }
 
 template <class Op>
@@ -499,15 +586,48 @@ static int reduce_dim1(float* out, const float* a, size_t rows, size_t cols, siz
     const unsigned ty = 256 / tx;
     const size_t gx = ceil_div(row_units, tx);
     // split columns into chunks so the grid has ~2 waves, but keep >= 8*ty columns per chunk
-    size_t nchunks = ceil_div(row_waves() * cap, gx);
+    size_t nchunks = ceil_div(row_waves(rows * cols) * cap, gx);
     const size_t min_cols = size_t(ty) * 8;
     if (nchunks * min_cols > cols) nchunks = cols / min_cols;
     if (nchunks < 1) nchunks = 1;
     if (nchunks > 65535) nchunks = 65535;
-    const size_t cpc = ceil_div(cols, nchunks);
+    size_t cpc = ceil_div(cols, nchunks);
     nchunks = ceil_div(cols, cpc);
     const size_t smem = size_t(ty) * tx * V * sizeof(float);
-    const dim3 grid((unsigned)gx, (unsigned)nchunks, 1), block(tx, ty, 1);
+    const dim3 block(tx, ty, 1);
+    static const bool no_cluster = std::getenv("JZ_REDUCE_NO_CLUSTER") != nullptr;
+    if (nchunks >= kRowCluster && gx <= kTicketSlots && !no_cluster) {
+        // one launch: clusters of 8 column chunks + last-CTA fold.  Round the chunk count up to a multiple of 8
+        // (trailing chunks past the last column contribute Op::init()).
+        const size_t nch = ceil_div(nchunks, size_t(kRowCluster)) * kRowCluster;
+        cpc = ceil_div(cols, nch);
+        unsigned* tickets = tickets_for(s);
+        if (!tickets) return fail(JZ_ERR_CUDA, "reduce: could not allocate the ticket counters");
+        void* partial = nullptr;
+        int rc = ws_alloc(&partial, (nch / kRowCluster) * rows * sizeof(float), s);
+        if (rc != JZ_OK) return rc;
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)gx, (unsigned)nch, 1);
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = kRowCluster;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        float* part = static_cast<float*>(partial);
+        cudaError_t e = vec ? cudaLaunchKernelEx(&cfg, rowreduce_kernel<Op, 4, true>, part, a, rows, cols, ld, cpc, out, tickets)
+                            : cudaLaunchKernelEx(&cfg, rowreduce_kernel<Op, 1, true>, part, a, rows, cols, ld, cpc, out, tickets);
+        ctx().launches.fetch_add(1, std::memory_order_relaxed);
+        ws_free(partial, s);
+        if (e != cudaSuccess) return cuda_fail(e, "rowreduce_kernel (cluster) launch");
+        return JZ_OK;
+    }
+    const dim3 grid((unsigned)gx, (unsigned)nchunks, 1);
     float* dst = out;
     void* partial = nullptr;
     if (nchunks > 1) {
@@ -515,8 +635,8 @@ static int reduce_dim1(float* out, const float* a, size_t rows, size_t cols, siz
         if (rc != JZ_OK) return rc;
         dst = static_cast<float*>(partial);
     }
-    if (vec) JZ_LAUNCH((rowreduce_kernel<Op, 4>), grid, block, smem, s, dst, a, rows, cols, ld, cpc);
-    else JZ_LAUNCH((rowreduce_kernel<Op, 1>), grid, block, smem, s, dst, a, rows, cols, ld, cpc);
+    if (vec) JZ_LAUNCH((rowreduce_kernel<Op, 4, false>), grid, block, smem, s, dst, a, rows, cols, ld, cpc, nullptr, nullptr);
+    else JZ_LAUNCH((rowreduce_kernel<Op, 1, false>), grid, block, smem, s, dst, a, rows, cols, ld, cpc, nullptr, nullptr);
     if (nchunks > 1) {
         // partial is rows x nchunks (col-major, ld = rows): fold across its columns
         int rc = reduce_dim1<Op>(out, dst, rows, nchunks, rows, s);

@@ -173,7 +173,7 @@ def test_reductions_vs_reference_fixture(jz, golden, name):
 
 @pytest.mark.parametrize("shape", [(1, 1), (1, 777), (777, 1), (31, 33), (32, 4096), (33, 4096), (4096, 33),
                                    (5, 100003), (100003, 5), (2048, 2048), (1001, 1001), (16, 1 << 18), (1 << 18, 16),
-                                   (70000, 3), (40000, 40)])
+                                   (70000, 3), (40000, 40), (4096, 4096), (8200, 1000), (260, 30000)])
 def test_sum_max_all_kernel_variants(jz, port, shape):
     rng = np.random.default_rng(shape[0] * 131 + shape[1])
     M = F(rng.standard_normal(shape))
@@ -184,6 +184,8 @@ def test_sum_max_all_kernel_variants(jz, port, shape):
         got = jz.sum(m, dim).to_host().ravel()
         assert np.all(np.abs(got - truth) <= 1e-5 * np.maximum(scale, 1e-30)), (shape, dim)
         assert same_bits(jz.colmax(m, dim).to_host().ravel(), M.max(axis=dim))
+        # no float atomics anywhere (cluster + ticket fold included): the same call gives the same bits
+        assert same_bits(jz.sum(m, dim).to_host().ravel(), got)
 
 
 def test_empty_reductions(jz):
