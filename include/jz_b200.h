@@ -168,8 +168,34 @@ int jz_gemm_chain_bcast(int transA, int transB, size_t m, size_t n, size_t k, fl
                         const float* A, size_t lda, const float* B, size_t ldb,
                         float* C, size_t ldc, float* const* peer_C, int n_peers,
                         const jz_step* steps, int nsteps, int mode, jz_stream_t stream);
-/* which kernel family the last jz_gemm used: 0 none, 1 tcgen05, 2 simt, 3 outer/gemv special case */
+/* strided batch: member i is C + i*strideC = alpha * op(A + i*strideA) * op(B + i*strideB) + beta * (C + i*strideC)
+ * (cublasSgemmStridedBatched in TransformerLayer's attention, ml/layer.hpp:2896-2926, 3089-3283) */
+int jz_gemm_strided_batched(int transA, int transB, size_t m, size_t n, size_t k, float alpha,
+                            const float* A, size_t lda, size_t strideA, const float* B, size_t ldb, size_t strideB,
+                            float beta, float* C, size_t ldc, size_t strideC, size_t batch, int mode, jz_stream_t stream);
+/* which kernel family the last jz_gemm used: 0 none, 1 tcgen05, 2 simt, 3 outer/gemv special case, 4 small-product */
 int jz_gemm_last_path(void);
+
+/* ---- transformer helper kernels (the reference's own __global__ kernels in ml/layer.hpp).
+ *      Attention scores: (seq_len, seq_len*batch) column-major, block i = the seq_len x seq_len matrix at
+ *      x + i*seq_len^2, element (query a, key b) at a + b*seq_len.  LayerNorm tensors: (dim, n) column-major. */
+/* y(a,:) = softmax over keys of x(a,:), per block; causal != 0 first replaces x(a,b), b > a, by mask_val
+   (softmax_rows_batched_kernel ml/layer.hpp:2373-2398 with causal_mask_kernel :2400-2412 fused; y may alias x) */
+int jz_softmax_rows_batched(float* y, const float* x, size_t seq_len, size_t batch, int causal, float mask_val,
+                            jz_stream_t stream);
+int jz_causal_mask(float* s_inout, size_t seq_len, size_t batch, float mask_val, jz_stream_t stream); /* :2400-2412 */
+/* dS(a,b) = A(a,b) * (dA(a,b) - sum_b' A(a,b') dA(a,b')) * scale, dA(a,b) = dAT[b + a*seq_len] per block
+   (softmax_backward_rows_kernel ml/layer.hpp:2418-2445) */
+int jz_softmax_rows_backward(float* dS, const float* A, const float* dAT, size_t seq_len, size_t batch, float scale,
+                             jz_stream_t stream);
+/* y = gamma .* xhat + beta, xhat = (x - mean)/sqrt(var + 1e-5) per column; also stores xhat and 1/sqrt(var + 1e-5)
+   (layernorm_forward_kernel ml/layer.hpp:2483-2510) */
+int jz_layernorm_forward(float* y, float* xhat, float* inv_std, const float* x, const float* gamma, const float* beta,
+                         size_t dim, size_t n, jz_stream_t stream);
+/* dx = inv_std .* (dxhat - mean(dxhat) - xhat .* mean(dxhat .* xhat)), dxhat = gamma .* dy
+   (layernorm_backward_kernel ml/layer.hpp:2514-2538) */
+int jz_layernorm_backward(float* dx, const float* dy, const float* gamma, const float* xhat, const float* inv_std,
+                          size_t dim, size_t n, jz_stream_t stream);
 
 /* ---- RNG (replaces cuRAND XORWOW, cumatrix.cu:354-420; counter-based Philox4x32-10) */
 int jz_rand_uniform(float* x, size_t n, uint64_t seed, uint64_t offset, jz_stream_t stream);

@@ -81,6 +81,13 @@ _SIGS = {
                               _F, c_size_t, POINTER(jz_step), c_int, c_int, _S]),
     "jz_gemm_chain_bcast": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, _F, c_size_t,
                                     _F, c_size_t, POINTER(c_void_p), c_int, POINTER(jz_step), c_int, c_int, _S]),
+    "jz_gemm_strided_batched": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, c_size_t, _F, c_size_t,
+                                        c_size_t, c_float, _F, c_size_t, c_size_t, c_size_t, c_int, _S]),
+    "jz_softmax_rows_batched": (c_int, [_F, _F, c_size_t, c_size_t, c_int, c_float, _S]),
+    "jz_causal_mask": (c_int, [_F, c_size_t, c_size_t, c_float, _S]),
+    "jz_softmax_rows_backward": (c_int, [_F, _F, _F, c_size_t, c_size_t, c_float, _S]),
+    "jz_layernorm_forward": (c_int, [_F, _F, _F, _F, _F, _F, c_size_t, c_size_t, _S]),
+    "jz_layernorm_backward": (c_int, [_F, _F, _F, _F, _F, c_size_t, c_size_t, _S]),
     "jz_rand_uniform": (c_int, [_F, c_size_t, c_uint64, c_uint64, _S]),
     "jz_rand_normal": (c_int, [_F, c_size_t, c_uint64, c_uint64, _S]),
     "jz_adam_update": (c_int, [_F, _F, _F, c_size_t] + [c_float] * 6 + [_S]),

@@ -41,7 +41,7 @@ namespace jz {
 bool gemm_small_wants(size_t m, size_t n, size_t k);
 int launch_gemm_small(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
                       const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain,
-                      cudaStream_t s);
+                      cudaStream_t s, size_t batch = 1, size_t strideA = 0, size_t strideB = 0, size_t strideC = 0);
 
 // ======================================================================= SIMT fallback
 constexpr int SBM = 64, SBN = 64, SBK = 16;
@@ -1015,6 +1015,34 @@ int jz_gemm(int transA, int transB, size_t m, size_t n, size_t k, float alpha, c
     ChainParams chain;
     chain.n = 0;
     return gemm_entry(transA, transB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, mode, as_stream(stream));
+}
+
+/* strided batch (cublasSgemmStridedBatched in TransformerLayer, ml/layer.hpp:2896-2926): member i uses
+   A + i*strideA, B + i*strideB, C + i*strideC.  Attention-sized members (seq x seq x head_dim) run as ONE launch of
+   the small-product kernel with the batch on grid.z; large members go through the single-product paths one by one. */
+int jz_gemm_strided_batched(int transA, int transB, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                            size_t strideA, const float* B, size_t ldb, size_t strideB, float beta, float* C, size_t ldc,
+                            size_t strideC, size_t batch, int mode, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    if (batch == 0 || m == 0 || n == 0) return JZ_OK;
+    if (!C) return fail(JZ_ERR_ARG, "jz_gemm_strided_batched: null C");
+    if (ldc < m) return fail(JZ_ERR_SHAPE, "jz_gemm_strided_batched: ldc < m");
+    if (k > 0) {
+        if (!A || !B) return fail(JZ_ERR_ARG, "jz_gemm_strided_batched: null operand");
+        if (lda < (transA ? k : m) || ldb < (transB ? n : k)) return fail(JZ_ERR_SHAPE, "jz_gemm_strided_batched: leading dimension too small");
+    }
+    ChainParams chain;
+    chain.n = 0;
+    cudaStream_t s = as_stream(stream);
+    const bool tc_shape = m >= 64 && n >= 64 && k >= 32 && double(m) * double(n) * double(k) >= double(1 << 24);
+    if (k >= 2 && !tc_shape && gemm_small_wants(m, n, k) && batch <= 65535)
+        return launch_gemm_small(transA, transB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s, batch, strideA, strideB, strideC);
+    for (size_t i = 0; i < batch; i++) {
+        int rc = gemm_entry(transA, transB, m, n, k, alpha, A + i * strideA, lda, B + i * strideB, ldb, beta, C + i * strideC, ldc,
+                            chain, mode, s);
+        if (rc != JZ_OK) return rc;
+    }
+    return JZ_OK;
 }
 
 int jz_gemm_chain(int transA, int transB, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,

@@ -85,10 +85,14 @@ template <bool TA, bool TB, int NT, bool KSPLIT, bool VEC, int SK_WARPS>
 __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, size_t n, size_t k, float alpha,
                                                                    const float* __restrict__ A, size_t lda,
                                                                    const float* __restrict__ B, size_t ldb, float beta,
-                                                                   float* C, size_t ldc, ChainParams chain_p) {
+                                                                   float* C, size_t ldc, ChainParams chain_p,
+                                                                   size_t strideA, size_t strideB, size_t strideC) {
     __shared__ ChainParams chain;
     __shared__ float red[KSPLIT ? SK_WARPS : 1][KSPLIT ? NT : 1][32];
     stage_chain(&chain, chain_p, threadIdx.x);
+    A += size_t(blockIdx.z) * strideA;   // strided batch (blockIdx.z = 0 for a single product)
+    B += size_t(blockIdx.z) * strideB;
+    C += size_t(blockIdx.z) * strideC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t i = size_t(blockIdx.x) * 32 + lane;
     const size_t il = i < m ? i : m - 1;   // clamped row for loads
@@ -156,25 +160,28 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
     }
 }
 
+struct SmallBatch { size_t count = 1, sA = 0, sB = 0, sC = 0; };
+
 template <bool TA, bool TB, int NT, bool KSPLIT, int W>
 static int launch_small_v(bool vec, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda, const float* B,
-                          size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain, cudaStream_t s) {
+                          size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain, const SmallBatch& bt,
+                          cudaStream_t s) {
     const size_t gx = ceil_div(m, size_t(32));
     const size_t gy = ceil_div(n, size_t(NT) * (KSPLIT ? 1 : W));
-    if (gy > 65535) return fail(JZ_ERR_UNSUPPORTED, "small gemm: n too large");
-    const dim3 grid((unsigned)gx, (unsigned)gy, 1);
-    if (vec) JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, true, W>), grid, 32 * W, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
-    else JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, false, W>), grid, 32 * W, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain);
+    if (gy > 65535 || bt.count > 65535) return fail(JZ_ERR_UNSUPPORTED, "small gemm: n or batch too large");
+    const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)bt.count);
+    if (vec) JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, true, W>), grid, 32 * W, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt.sA, bt.sB, bt.sC);
+    else JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, false, W>), grid, 32 * W, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt.sA, bt.sB, bt.sC);
     return JZ_OK;
 }
 // variants: k split over 8 / 16 / 32 warps, 8-column blocks
 template <bool TA, bool TB>
 static int launch_small_cfg(bool ksplit, int warps, int nt, bool vec, size_t m, size_t n, size_t k, float alpha,
                             const float* A, size_t lda, const float* B, size_t ldb, float beta, float* C, size_t ldc,
-                            const ChainParams& chain, cudaStream_t s) {
+                            const ChainParams& chain, const SmallBatch& bt, cudaStream_t s) {
 #define JZ_SMALL_CASE(KS, W, NT_) \
     if (ksplit == KS && warps == W && nt == NT_) \
-        return launch_small_v<TA, TB, NT_, KS, W>(vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+        return launch_small_v<TA, TB, NT_, KS, W>(vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt, s);
     JZ_SMALL_CASE(true, 8, 8) JZ_SMALL_CASE(true, 16, 8) JZ_SMALL_CASE(true, 32, 8)
 #undef JZ_SMALL_CASE
     return fail(JZ_ERR_ARG, "small gemm: no kernel variant for ksplit=%d warps=%d nt=%d", int(ksplit), warps, nt);
@@ -194,9 +201,12 @@ static int env_int(const char* name) {
 
 int launch_gemm_small(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
                       const float* B, size_t ldb, float beta, float* C, size_t ldc, const ChainParams& chain,
-                      cudaStream_t s) {
-    // 128-bit operand loads need 16-byte phase on the k (or column) runs they cover
-    const bool vec = (!ta || (lda % 4 == 0 && aligned16(A))) && ldb % 4 == 0 && aligned16(B);
+                      cudaStream_t s, size_t batch, size_t strideA, size_t strideB, size_t strideC) {
+    SmallBatch bt;
+    bt.count = batch; bt.sA = strideA; bt.sB = strideB; bt.sC = strideC;
+    // 128-bit operand loads need 16-byte phase on the k (or column) runs they cover (every batch member included)
+    const bool vec = (!ta || (lda % 4 == 0 && aligned16(A))) && ldb % 4 == 0 && aligned16(B) &&
+                     (batch <= 1 || ((!ta || strideA % 4 == 0) && strideB % 4 == 0));
     static const int f_warps = env_int("JZ_SMALL_WARPS");
     const bool ksplit = true;
     const int nt = 8;
@@ -204,10 +214,10 @@ int launch_gemm_small(int ta, int tb, size_t m, size_t n, size_t k, float alpha,
     int warps = k >= 512 ? 32 : (k >= 128 ? 16 : 8);
     if (f_warps == 8 || f_warps == 16 || f_warps == 32) warps = f_warps;
     int rc;
-    if (!ta && !tb) rc = launch_small_cfg<false, false>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
-    else if (ta && !tb) rc = launch_small_cfg<true, false>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
-    else if (!ta && tb) rc = launch_small_cfg<false, true>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
-    else rc = launch_small_cfg<true, true>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, s);
+    if (!ta && !tb) rc = launch_small_cfg<false, false>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt, s);
+    else if (ta && !tb) rc = launch_small_cfg<true, false>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt, s);
+    else if (!ta && tb) rc = launch_small_cfg<false, true>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt, s);
+    else rc = launch_small_cfg<true, true>(ksplit, warps, nt, vec, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt, s);
     if (rc == JZ_OK) ctx().gemm_last_path = 4;
     return rc;
 }

@@ -151,6 +151,39 @@ class Oracle:
                                     c_double(nb), _f(out))
         return out
 
+    # ---- transformer helper kernels (port only; see the PARITY UNPINNED note in jz_oracle.c)
+    def softmax_rows_batched(self, x, S, batch, causal=False, mask_val=-1e9):
+        x = np.ascontiguousarray(x, dtype=np.float32).ravel()
+        y = np.empty_like(x)
+        self._fn("softmax_rows_batched")(_f(x), _f(y), c_size_t(S), c_size_t(batch), c_int(int(causal)), c_float(mask_val))
+        return y
+
+    def softmax_rows_backward(self, A, dAT, S, batch, scale):
+        A = np.ascontiguousarray(A, dtype=np.float32).ravel()
+        dAT = np.ascontiguousarray(dAT, dtype=np.float32).ravel()
+        dS = np.empty_like(A)
+        self._fn("softmax_rows_backward")(_f(A), _f(dAT), _f(dS), c_size_t(S), c_size_t(batch), c_float(scale))
+        return dS
+
+    def layernorm_forward(self, x, gamma, beta):
+        x = _phys(x)
+        dim, N = x.shape
+        gamma = np.ascontiguousarray(gamma, dtype=np.float32).ravel()
+        beta = np.ascontiguousarray(beta, dtype=np.float32).ravel()
+        y, xhat = np.empty_like(x, order="F"), np.empty_like(x, order="F")
+        inv = np.empty(N, dtype=np.float32)
+        self._fn("layernorm_forward")(_f(x), _f(gamma), _f(beta), _f(y), _f(xhat), _f(inv), c_size_t(dim), c_size_t(N))
+        return y, xhat, inv
+
+    def layernorm_backward(self, dy, gamma, xhat, inv_std):
+        dy, xhat = _phys(dy), _phys(xhat)
+        dim, N = dy.shape
+        gamma = np.ascontiguousarray(gamma, dtype=np.float32).ravel()
+        inv_std = np.ascontiguousarray(inv_std, dtype=np.float32).ravel()
+        dx = np.empty_like(dy, order="F")
+        self._fn("layernorm_backward")(_f(dy), _f(gamma), _f(xhat), _f(inv_std), _f(dx), c_size_t(dim), c_size_t(N))
+        return dx
+
     def norm(self, x):
         x = np.ascontiguousarray(x, dtype=np.float32)
         return float(self._fn("norm", c_float)(_f(x), c_size_t(x.size)))
