@@ -49,7 +49,7 @@ PROGRAMS = [
     ("pagerank", "examples/pagerank.cu", []),
 ]
 # this repository's own C++ tests (same compute() convention), staged next to the reference's tests
-OWN_TESTS = [("test_fusion", "test_fusion.cu")]
+OWN_TESTS = [("test_fusion", "test_fusion.cu"), ("bench_attention", "bench_attention.cu")]
 OURS_IN_CPP = {"cumatrix.cuh", "memory.hpp", "jz_lazy.hpp"}
 REF_CPP = ["core.hpp", "matrix.hpp", "operators.hpp", "helper.hpp", "juzhen.hpp", "cpulinalg.hpp"]
 

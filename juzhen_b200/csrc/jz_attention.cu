@@ -16,8 +16,8 @@ namespace jz {
 
 constexpr int AT_WARPS = 8;
 
-// fold one float per (lane, warp) over the warps of the CTA; result valid in every thread
-template <class F>
+// fold one float per (lane, warp) over the W warps of the CTA; result valid in every thread
+template <int W, class F>
 __device__ __forceinline__ float fold_warps(float v, float (*red)[32], F f, float init) {
     const int lane = threadIdx.x, w = threadIdx.y;
     __syncthreads();   // previous use of `red` is over
@@ -25,7 +25,7 @@ __device__ __forceinline__ float fold_warps(float v, float (*red)[32], F f, floa
     __syncthreads();
     float t = init;
 #pragma unroll
-    for (int q = 0; q < AT_WARPS; q++) t = f(t, red[q][lane]);
+    for (int q = 0; q < W; q++) t = f(t, red[q][lane]);
     return t;
 }
 
@@ -33,24 +33,26 @@ __device__ __forceinline__ float fold_warps(float v, float (*red)[32], F f, floa
 // grid (ceil(S/32), batch), block (32, 8): lanes own rows, warps stride over keys.  STAGED: the 32 x S tile is kept
 // in shared memory (S*128 bytes) between the max, exp-sum and normalise passes; otherwise y is the scratch, as in
 // the reference.  ml/layer.hpp:2373-2398 (+ causal_mask_kernel :2400-2412 fused as a flag).
-template <bool CAUSAL, bool STAGED>
-__global__ void __launch_bounds__(32 * AT_WARPS) softmax_rows_kernel(float* y, const float* x, int S, float mask_val) {
+template <bool CAUSAL, bool STAGED, int W>
+__global__ void __launch_bounds__(32 * W) softmax_rows_kernel(float* y, const float* x, int S, float mask_val) {
     extern __shared__ float tile[];   // [S][32] when STAGED
-    __shared__ float red[AT_WARPS][32];
+    __shared__ float red[W][32];
     const int lane = threadIdx.x, w = threadIdx.y;
     const int a = blockIdx.x * 32 + lane;
     const bool ok = a < S;
     const size_t base = size_t(blockIdx.y) * size_t(S) * size_t(S) + size_t(ok ? a : 0);
     float m = -1e30f;
-    for (int b = w; b < S; b += AT_WARPS) {
+#pragma unroll 8
+    for (int b = w; b < S; b += W) {
         float v = x[base + size_t(b) * S];
         if (CAUSAL && b > a) v = mask_val;
         if (STAGED) tile[b * 32 + lane] = v;
         m = m > v ? m : v;
     }
-    m = fold_warps(m, red, [](float p, float q) { return p > q ? p : q; }, -1e30f);
+    m = fold_warps<W>(m, red, [](float p, float q) { return p > q ? p : q; }, -1e30f);
     float s = 0.0f;
-    for (int b = w; b < S; b += AT_WARPS) {
+#pragma unroll 8
+    for (int b = w; b < S; b += W) {
         float v;
         if (STAGED) v = tile[b * 32 + lane];
         else { v = x[base + size_t(b) * S]; if (CAUSAL && b > a) v = mask_val; }
@@ -59,10 +61,11 @@ __global__ void __launch_bounds__(32 * AT_WARPS) softmax_rows_kernel(float* y, c
         else if (ok) y[base + size_t(b) * S] = e;
         s += e;
     }
-    s = fold_warps(s, red, [](float p, float q) { return p + q; }, 0.0f);
+    s = fold_warps<W>(s, red, [](float p, float q) { return p + q; }, 0.0f);
     const float inv = 1.0f / (s + 1e-12f);
     if (!ok) return;
-    for (int b = w; b < S; b += AT_WARPS) {
+#pragma unroll 8
+    for (int b = w; b < S; b += W) {
         const float e = STAGED ? tile[b * 32 + lane] : y[base + size_t(b) * S];
         y[base + size_t(b) * S] = e * inv;
     }
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(32 * AT_WARPS) softmax_rows_backward_kernel(fl
     // stage: warp w copies columns a_local = w, w + 8, ... of dAT (each S contiguous floats), lanes along b
     for (int al = w; al < 32; al += AT_WARPS) {
         const int a = a0 + al;
+#pragma unroll 8
         for (int b = lane; b < S; b += 32) dtile[b * 33 + al] = a < S ? dAT[blk + size_t(a) * S + b] : 0.0f;
     }
     __syncthreads();
@@ -97,9 +101,11 @@ __global__ void __launch_bounds__(32 * AT_WARPS) softmax_rows_backward_kernel(fl
     const bool ok = a < S;
     const size_t base = blk + size_t(ok ? a : 0);
     float rs = 0.0f;
+#pragma unroll 8
     for (int b = w; b < S; b += AT_WARPS) rs += A[base + size_t(b) * S] * dtile[b * 33 + lane];
-    rs = fold_warps(rs, red, [](float p, float q) { return p + q; }, 0.0f);
+    rs = fold_warps<AT_WARPS>(rs, red, [](float p, float q) { return p + q; }, 0.0f);
     if (!ok) return;
+#pragma unroll 8
     for (int b = w; b < S; b += AT_WARPS) {
         const float av = A[base + size_t(b) * S];
         dS[base + size_t(b) * S] = av * (dtile[b * 33 + lane] - rs) * scale;
@@ -115,28 +121,60 @@ __device__ __forceinline__ float warp_sum(float v) {
 // One WARP per column c of the (dim, N) tensor (ml/layer.hpp:2483-2510):
 //   mu = mean(x_c), var = mean((x_c - mu)^2), inv = rsqrt(var + 1e-5), xhat = (x - mu)*inv, y = gamma*xhat + beta.
 // The column is re-read from L1 for the second and third pass (it was just loaded); HBM sees one read, two writes.
+// VEC: dim % 4 == 0 and 16-byte aligned tensors -> 128-bit accesses.
+template <bool VEC>
 __global__ void __launch_bounds__(32 * AT_WARPS) layernorm_forward_kernel(float* y, float* xhat, float* inv_std, const float* x,
                                                                           const float* gamma, const float* beta, int dim, size_t N) {
     const int lane = threadIdx.x;
     const size_t c = size_t(blockIdx.x) * AT_WARPS + threadIdx.y;
     if (c >= N) return;
     const float* xc = x + c * size_t(dim);
-    float mu = 0.0f;
-    for (int i = lane; i < dim; i += 32) mu += xc[i];
-    mu = warp_sum(mu) / dim;
-    float var = 0.0f;
-    for (int i = lane; i < dim; i += 32) { const float d = xc[i] - mu; var += d * d; }
+    float mu = 0.0f, var = 0.0f;
+    if constexpr (VEC) {
+        const float4* x4 = reinterpret_cast<const float4*>(xc);
+        const int d4 = dim >> 2;
+#pragma unroll 4
+        for (int i = lane; i < d4; i += 32) { const float4 v = x4[i]; mu += (v.x + v.y) + (v.z + v.w); }
+        mu = warp_sum(mu) / dim;
+#pragma unroll 4
+        for (int i = lane; i < d4; i += 32) {
+            const float4 v = x4[i];
+            const float a0 = v.x - mu, a1 = v.y - mu, a2 = v.z - mu, a3 = v.w - mu;
+            var += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        }
+    } else {
+        for (int i = lane; i < dim; i += 32) mu += xc[i];
+        mu = warp_sum(mu) / dim;
+        for (int i = lane; i < dim; i += 32) { const float d = xc[i] - mu; var += d * d; }
+    }
     var = warp_sum(var) / dim;
     const float inv = rsqrtf(var + 1e-5f);
     if (lane == 0) inv_std[c] = inv;
-    for (int i = lane; i < dim; i += 32) {
-        const float xh = (xc[i] - mu) * inv;
-        xhat[c * size_t(dim) + i] = xh;
-        y[c * size_t(dim) + i] = gamma[i] * xh + beta[i];
+    if constexpr (VEC) {
+        const float4* x4 = reinterpret_cast<const float4*>(xc);
+        const float4* g4 = reinterpret_cast<const float4*>(gamma);
+        const float4* b4 = reinterpret_cast<const float4*>(beta);
+        float4* h4 = reinterpret_cast<float4*>(xhat + c * size_t(dim));
+        float4* y4 = reinterpret_cast<float4*>(y + c * size_t(dim));
+        const int d4 = dim >> 2;
+#pragma unroll 4
+        for (int i = lane; i < d4; i += 32) {
+            const float4 v = x4[i], g = g4[i], b = b4[i];
+            const float4 h = make_float4((v.x - mu) * inv, (v.y - mu) * inv, (v.z - mu) * inv, (v.w - mu) * inv);
+            h4[i] = h;
+            y4[i] = make_float4(g.x * h.x + b.x, g.y * h.y + b.y, g.z * h.z + b.z, g.w * h.w + b.w);
+        }
+    } else {
+        for (int i = lane; i < dim; i += 32) {
+            const float xh = (xc[i] - mu) * inv;
+            xhat[c * size_t(dim) + i] = xh;
+            y[c * size_t(dim) + i] = gamma[i] * xh + beta[i];
+        }
     }
 }
 
 // dx = inv_std * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), dxhat = gamma * dy (ml/layer.hpp:2514-2538)
+template <bool VEC>
 __global__ void __launch_bounds__(32 * AT_WARPS) layernorm_backward_kernel(float* dx, const float* dy, const float* gamma,
                                                                            const float* xhat, const float* inv_std, int dim, size_t N) {
     const int lane = threadIdx.x;
@@ -144,6 +182,30 @@ __global__ void __launch_bounds__(32 * AT_WARPS) layernorm_backward_kernel(float
     if (c >= N) return;
     const size_t c0 = c * size_t(dim);
     float m1 = 0.0f, m2 = 0.0f;
+    if constexpr (VEC) {
+        const float4* g4 = reinterpret_cast<const float4*>(gamma);
+        const float4* d4p = reinterpret_cast<const float4*>(dy + c0);
+        const float4* h4 = reinterpret_cast<const float4*>(xhat + c0);
+        float4* o4 = reinterpret_cast<float4*>(dx + c0);
+        const int d4 = dim >> 2;
+#pragma unroll 4
+        for (int i = lane; i < d4; i += 32) {
+            const float4 g = g4[i], d = d4p[i], h = h4[i];
+            const float t0 = __fmul_rn(g.x, d.x), t1 = __fmul_rn(g.y, d.y), t2 = __fmul_rn(g.z, d.z), t3 = __fmul_rn(g.w, d.w);
+            m1 += (t0 + t1) + (t2 + t3);
+            m2 += (t0 * h.x + t1 * h.y) + (t2 * h.z + t3 * h.w);
+        }
+        m1 = warp_sum(m1) / dim;
+        m2 = warp_sum(m2) / dim;
+        const float inv = inv_std[c];
+#pragma unroll 4
+        for (int i = lane; i < d4; i += 32) {
+            const float4 g = g4[i], d = d4p[i], h = h4[i];
+            const float t0 = __fmul_rn(g.x, d.x), t1 = __fmul_rn(g.y, d.y), t2 = __fmul_rn(g.z, d.z), t3 = __fmul_rn(g.w, d.w);
+            o4[i] = make_float4(inv * (t0 - m1 - h.x * m2), inv * (t1 - m1 - h.y * m2), inv * (t2 - m1 - h.z * m2), inv * (t3 - m1 - h.w * m2));
+        }
+        return;
+    }
     for (int i = lane; i < dim; i += 32) {
         const float dxh = __fmul_rn(gamma[i], dy[c0 + i]);   // one rounding, the same in both passes
         m1 += dxh;
@@ -153,7 +215,7 @@ __global__ void __launch_bounds__(32 * AT_WARPS) layernorm_backward_kernel(float
     m2 = warp_sum(m2) / dim;
     const float inv = inv_std[c];
     for (int i = lane; i < dim; i += 32) {
-        const float dxh = __fmul_rn(gamma[i], dy[c0 + i]);   // one rounding, the same in both passes
+        const float dxh = __fmul_rn(gamma[i], dy[c0 + i]);
         dx[c0 + i] = inv * (dxh - m1 - xhat[c0 + i] * m2);
     }
 }
@@ -173,21 +235,25 @@ int jz_softmax_rows_batched(float* y, const float* x, size_t seq_len, size_t bat
     if (!y || !x) return fail(JZ_ERR_ARG, "jz_softmax_rows_batched: null pointer");
     if (seq_len >= (size_t(1) << 30) || batch > 65535) return fail(JZ_ERR_UNSUPPORTED, "jz_softmax_rows_batched: shape too large");
     cudaStream_t s = as_stream(stream);
-    const dim3 grid((unsigned)ceil_div(seq_len, size_t(32)), (unsigned)batch, 1), block(32, AT_WARPS, 1);
+    const dim3 grid((unsigned)ceil_div(seq_len, size_t(32)), (unsigned)batch, 1);
     const size_t smem = seq_len * 32 * sizeof(float);
     const int S = int(seq_len);
-    if (smem <= kMaxDynSmem) {
+    // The tile stays in shared memory while several CTAs still fit on an SM (S <= 512: 64 KB); longer rows use y as the
+    // scratch (second and third pass are L2 hits) with 16 warps per CTA, so enough loads are in flight.
+    if (smem <= 64 * 1024) {
         static bool attr_done = false;
         if (!attr_done) {
-            JZ_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem)));
-            JZ_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem)));
+            JZ_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<true, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            JZ_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<false, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             attr_done = true;
         }
-        if (causal) JZ_LAUNCH((softmax_rows_kernel<true, true>), grid, block, smem, s, y, x, S, mask_val);
-        else JZ_LAUNCH((softmax_rows_kernel<false, true>), grid, block, smem, s, y, x, S, mask_val);
+        const dim3 block(32, 8, 1);
+        if (causal) JZ_LAUNCH((softmax_rows_kernel<true, true, 8>), grid, block, smem, s, y, x, S, mask_val);
+        else JZ_LAUNCH((softmax_rows_kernel<false, true, 8>), grid, block, smem, s, y, x, S, mask_val);
     } else {
-        if (causal) JZ_LAUNCH((softmax_rows_kernel<true, false>), grid, block, 0, s, y, x, S, mask_val);
-        else JZ_LAUNCH((softmax_rows_kernel<false, false>), grid, block, 0, s, y, x, S, mask_val);
+        const dim3 block(32, 16, 1);
+        if (causal) JZ_LAUNCH((softmax_rows_kernel<true, false, 16>), grid, block, 0, s, y, x, S, mask_val);
+        else JZ_LAUNCH((softmax_rows_kernel<false, false, 16>), grid, block, 0, s, y, x, S, mask_val);
     }
     return JZ_OK;
 }
@@ -226,7 +292,9 @@ int jz_layernorm_forward(float* y, float* xhat, float* inv_std, const float* x, 
     if (!y || !xhat || !inv_std || !x || !gamma || !beta) return fail(JZ_ERR_ARG, "jz_layernorm_forward: null pointer");
     if (dim >= (size_t(1) << 31)) return fail(JZ_ERR_UNSUPPORTED, "jz_layernorm_forward: dim too large");
     const dim3 grid((unsigned)ceil_div(n, size_t(AT_WARPS)), 1, 1), block(32, AT_WARPS, 1);
-    JZ_LAUNCH(layernorm_forward_kernel, grid, block, 0, as_stream(stream), y, xhat, inv_std, x, gamma, beta, int(dim), n);
+    const bool vec = dim % 4 == 0 && aligned16(y) && aligned16(xhat) && aligned16(x) && aligned16(gamma) && aligned16(beta);
+    if (vec) JZ_LAUNCH(layernorm_forward_kernel<true>, grid, block, 0, as_stream(stream), y, xhat, inv_std, x, gamma, beta, int(dim), n);
+    else JZ_LAUNCH(layernorm_forward_kernel<false>, grid, block, 0, as_stream(stream), y, xhat, inv_std, x, gamma, beta, int(dim), n);
     return JZ_OK;
 }
 
@@ -237,7 +305,9 @@ int jz_layernorm_backward(float* dx, const float* dy, const float* gamma, const 
     if (!dx || !dy || !gamma || !xhat || !inv_std) return fail(JZ_ERR_ARG, "jz_layernorm_backward: null pointer");
     if (dim >= (size_t(1) << 31)) return fail(JZ_ERR_UNSUPPORTED, "jz_layernorm_backward: dim too large");
     const dim3 grid((unsigned)ceil_div(n, size_t(AT_WARPS)), 1, 1), block(32, AT_WARPS, 1);
-    JZ_LAUNCH(layernorm_backward_kernel, grid, block, 0, as_stream(stream), dx, dy, gamma, xhat, inv_std, int(dim), n);
+    const bool vec = dim % 4 == 0 && aligned16(dx) && aligned16(dy) && aligned16(gamma) && aligned16(xhat);
+    if (vec) JZ_LAUNCH(layernorm_backward_kernel<true>, grid, block, 0, as_stream(stream), dx, dy, gamma, xhat, inv_std, int(dim), n);
+    else JZ_LAUNCH(layernorm_backward_kernel<false>, grid, block, 0, as_stream(stream), dx, dy, gamma, xhat, inv_std, int(dim), n);
     return JZ_OK;
 }
 
