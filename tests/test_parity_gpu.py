@@ -287,6 +287,26 @@ def test_broadcast_idioms(jz, port):
 
 
 # ------------------------------------------------------------------ pool + rng + adam
+@pytest.mark.parametrize("count", [1, 1000, (1 << 17) - 3, 1 << 17, (1 << 17) + 5, 1 << 20])
+def test_staged_upload_is_bit_exact_and_source_is_free_on_return(jz, count):
+    """jz_upload (pinned staging ring, 16 slots of 512 KiB; larger copies take the plain path): more uploads than slots,
+    the pageable source scribbled over right after each call, bit-exact contents on the device"""
+    L = jz.lib()
+    rng = np.random.default_rng(count)
+    keep, devs = [], []
+    src = np.empty(count, dtype=np.float32)
+    for i in range(40):
+        data = rng.standard_normal(count).astype(np.float32)
+        src[:] = data
+        d = jz.CM.empty("u", count, 1)
+        jz._lib.check(L.jz_upload(d.ptr, src.ctypes.data, count, None))
+        src[:] = -1.0            # the caller's buffer is free again as soon as the call returns
+        keep.append(data)
+        devs.append(d)
+    for data, d in zip(keep, devs):
+        assert same_bits(d.to_host().ravel(), data)
+
+
 def test_pool_reuses_exact_size_blocks(jz):
     import ctypes
     L = jz.lib()
