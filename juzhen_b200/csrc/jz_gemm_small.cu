@@ -7,9 +7,9 @@
 // microseconds of one SM row.  A classic shared-memory-tiled kernel serialises global-load latency once per k-tile
 // (measured on B200: 70-90 us for the two forward products above, 57 % of the demo_mnist step).  Here instead:
 //   * a WARP owns 32 rows x 8 columns of C for a slice of k, its lanes own the rows: A is read with one
-//     coalesced 128-byte load per k (plain A) or one 128-bit load per lane per 4 k (flagged-transpose A), B with
-//     warp-uniform 128-bit loads served by L1 (4 k per load for plain B, 4 columns per load for flagged B);
-//     no shared memory and no barrier inside the k loop;
+//     coalesced 128-byte load per k (plain A) or one 128-bit load per lane per 4 k (flagged-transpose A); the
+//     4 k x 8 columns of B an iteration needs are one element per lane, loaded once and shared by shuffle;
+//     no shared memory and no barrier inside the k loop, several iterations' loads in flight;
 //   * the 8 / 16 / 32 warps of a CTA split k (every iteration of a warp is one memory round trip, so deep
 //     products want many short slices); the partial tiles meet in shared memory once, at the end, and are
 //     summed in a fixed order -> deterministic results;
@@ -40,44 +40,25 @@ __device__ __forceinline__ void sk_load_a(float (&a)[4], const float* __restrict
     }
 }
 
-// acc[j] += sum_q a[q] * op(B)(kk + q, j0 + j), j < NT.  Every address is warp-uniform.
-template <bool TB, bool VEC, int NT>
-__device__ __forceinline__ void sk_fma_b(float (&acc)[NT], const float (&a)[4], const float* __restrict__ B, size_t ldb,
-                                         size_t kk, size_t j0, size_t n) {
-    if constexpr (!TB) {   // B(kk, j) at j*ldb + kk: contiguous in k
+// The 4 k x 8 columns of op(B) one iteration needs are exactly one float per lane: each lane loads ONE element
+// (plain B: lane = 4*j + q reads B[(j0+j)*ldb + kk + q], eight 16-byte runs; flagged B: lane = 8*q + j reads
+// B[(kk+q)*ldb + j0 + j], four 32-byte runs) and the warp shares them by shuffle.  One load instruction per
+// iteration instead of eight warp-uniform 128-bit loads, and one live register instead of 32: with 4 A loads that
+// is 5 loads per iteration, so several iterations' loads fit in flight even under the 64-register budget of a
+// 1024-thread CTA (the uniform-load form interleaved its loads with the FMAs and paid ~5 round trips per iteration).
+template <bool TB, int NT>
+__device__ __forceinline__ float sk_load_b(const float* __restrict__ B, size_t ldb, size_t kk, size_t j0, size_t n, int lane) {
+    static_assert(NT == 8, "one B element per lane: 4 k x 8 columns");
+    const int q = TB ? lane >> 3 : lane & 3, j = TB ? lane & 7 : lane >> 2;
+    const size_t jj = j0 + j < n ? j0 + j : n - 1;   // clamped: surplus columns are computed, never stored
+    return TB ? B[(kk + q) * ldb + jj] : B[jj * ldb + kk + q];
+}
+template <bool TB, int NT>
+__device__ __forceinline__ void sk_fma_b(float (&acc)[NT], const float (&a)[4], float bval) {
 #pragma unroll
-        for (int j = 0; j < NT; j++) {
-            const size_t jj = j0 + j < n ? j0 + j : n - 1;   // clamped: surplus columns are computed, never stored
-            float b[4];
-            if constexpr (VEC) {
-                const float4 v = *reinterpret_cast<const float4*>(B + jj * ldb + kk);
-                b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
-            } else {
+    for (int j = 0; j < NT; j++)
 #pragma unroll
-                for (int q = 0; q < 4; q++) b[q] = B[jj * ldb + kk + q];
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) acc[j] = fmaf(a[q], b[q], acc[j]);
-        }
-    } else {               // B(kk, j) at kk*ldb + j: contiguous in j
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float* row = B + (kk + q) * ldb;
-#pragma unroll
-            for (int j = 0; j < NT; j += 4) {
-                float b[4];
-                if (VEC && j0 + j + 3 < n) {
-                    const float4 v = *reinterpret_cast<const float4*>(row + j0 + j);
-                    b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 4; t++) b[t] = row[j0 + j + t < n ? j0 + j + t : n - 1];
-                }
-#pragma unroll
-                for (int t = 0; t < 4; t++) acc[j + t] = fmaf(a[q], b[t], acc[j + t]);
-            }
-        }
-    }
+        for (int q = 0; q < 4; q++) acc[j] = fmaf(a[q], __shfl_sync(0xffffffffu, bval, TB ? 8 * q + j : 4 * j + q), acc[j]);
 }
 
 // KSPLIT: the CTA's warps split k (true) or take different column blocks (false).
@@ -108,11 +89,12 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
     for (int j = 0; j < NT; j++) acc[j] = 0.0f;
     if (KSPLIT || j0 < n) {
         size_t kk = kbeg;
-#pragma unroll 2
+#pragma unroll 4
         for (; kk + 4 <= kend; kk += 4) {
             float a[4];
             sk_load_a<TA, VEC>(a, A, lda, il, kk);
-            sk_fma_b<TB, VEC, NT>(acc, a, B, ldb, kk, j0, n);
+            const float bval = sk_load_b<TB, NT>(B, ldb, kk, j0, n, lane);
+            sk_fma_b<TB, NT>(acc, a, bval);
         }
         for (; kk < kend; kk++) {   // k tail, one at a time
             const float a = TA ? A[il * lda + kk] : A[kk * lda + il];
@@ -204,9 +186,8 @@ int launch_gemm_small(int ta, int tb, size_t m, size_t n, size_t k, float alpha,
                       cudaStream_t s, size_t batch, size_t strideA, size_t strideB, size_t strideC) {
     SmallBatch bt;
     bt.count = batch; bt.sA = strideA; bt.sB = strideB; bt.sC = strideC;
-    // 128-bit operand loads need 16-byte phase on the k (or column) runs they cover (every batch member included)
-    const bool vec = (!ta || (lda % 4 == 0 && aligned16(A))) && ldb % 4 == 0 && aligned16(B) &&
-                     (batch <= 1 || ((!ta || strideA % 4 == 0) && strideB % 4 == 0));
+    // the 128-bit loads of a flagged-transpose A need 16-byte phase on its k runs (every batch member included)
+    const bool vec = !ta || (lda % 4 == 0 && aligned16(A) && (batch <= 1 || strideA % 4 == 0));
     static const int f_warps = env_int("JZ_SMALL_WARPS");
     const bool ksplit = true;
     const int nt = 8;
