@@ -298,6 +298,20 @@ def run_ours(args):
                 gemm[f"{mode_name}_{gn}"] = {"TFLOP/s": round(tf, 1), "ms": round(ms, 3), "roofline_peak": round(peak * world, 1),
                                              "frac": round(tf / (peak * world), 3), "path": L.jz_gemm_last_path()}
             del a, b, c
+            # measurement only (never on the product path): what the vendor library reaches on this box for the same
+            # product, as a cross-check of the assumed TF32 peak (MEASURED_PEAKS.json has no TF32 figure)
+            try:
+                old = torch.backends.cuda.matmul.allow_tf32
+                ta_, tb_ = torch.randn(gn, gn, device="cuda"), torch.randn(gn, gn, device="cuda")
+                for allow, key in ((True, "cublas_tf32"), (False, "cublas_fp32")):
+                    torch.backends.cuda.matmul.allow_tf32 = allow
+                    ms, _ = timed(lambda: torch.matmul(ta_, tb_), max(3, args.steps // 2), 2)
+                    gemm[f"{key}_{gn}"] = {"TFLOP/s": round(2.0 * gn ** 3 / (ms * 1e-3) / 1e12 * world, 1), "ms": round(ms, 3),
+                                           "note": "torch.matmul (cuBLAS) on the same box: comparison bar, not our kernel"}
+                torch.backends.cuda.matmul.allow_tf32 = old
+                del ta_, tb_
+            except Exception as e:  # noqa: BLE001
+                gemm[f"cublas_{gn}"] = {"error": str(e)[:120]}
 
     clk = clocks.stop() if rank == 0 else None   # sampled across every timed region above (sweep, per-op, e2e, GEMM)
     sharded = None
@@ -324,6 +338,7 @@ def run_ours(args):
                        "l2": "inputs (1 GiB/operand) larger than L2, no flush", "ops": [n for n, _ in SWEEP],
                        "algorithmic_bytes_per_step": sw.bytes_per_step, "parallelism": f"independent shards x{world}"},
             "frac_of_hbm_peak": round(value / world / pk["hbm_gbs"], 3),
+            "frac_of_8TBs_spec": round(value / world / 8000.0, 3),
             "roofline": roofline, "ops": per_op, "gemm": gemm, "sharded_gemm": sharded, "mnist_step": mnist, "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk, "cpu_baseline": cpu,
