@@ -47,6 +47,10 @@ PROGRAMS = [
     ("demo_mnist", "examples/demo_mnist.cu", []),
     ("knn", "examples/knn.cu", []),
     ("pagerank", "examples/pagerank.cu", []),
+    # the reference's own operator benchmark: ConvLayer (cuDNN) and TransformerLayer (its own kernels + cuBLAS batched
+    # GEMM on global_handle) ride on this backend's Matrix<CUDAfloat> unchanged -- out-of-scope code paths, built to
+    # show that they still work; needs the legacy cuBLAS handle in the launcher
+    ("benchmarkCoreOps", "tests/benchmarkCoreOps.cu", ["-DCUDNN_AVAILABLE", "-DJZ_LEGACY_CUBLAS_HANDLE", "-lcudnn", "-lcublas"]),
 ]
 # this repository's own C++ tests (same compute() convention), staged next to the reference's tests
 OWN_TESTS = [("test_fusion", "test_fusion.cu"), ("bench_attention", "bench_attention.cu")]
@@ -140,6 +144,11 @@ def build(only=None, force=False):
         if force or not newer(o, ours):
             run([NVCC, *fl, "-c", os.path.join(STAGE, "cpp", unit + ".cu"), "-o", o], f"compile {unit}.cu")
         objs.append(o)
+    # launcher variant that creates Matrix<CUDAfloat>::global_handle for code that calls cuBLAS itself
+    launcher_cublas = os.path.join(OBJ, "launcher_cublas.o")
+    if force or not newer(launcher_cublas, ours):
+        run([NVCC, *fl, "-DJZ_LEGACY_CUBLAS_HANDLE", "-c", os.path.join(STAGE, "cpp", "launcher.cu"), "-o", launcher_cublas],
+            "compile launcher.cu (legacy cuBLAS handle)")
     libdir = os.path.join(ROOT, "juzhen_b200")
     # RPATH (not RUNPATH) so OpenBLAS' private libgfortran next to it is found transitively
     link_flags = ["-Xlinker", "--disable-new-dtags", "-L", libdir, "-ljz_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../../juzhen_b200",
@@ -150,7 +159,8 @@ def build(only=None, force=False):
         exe = os.path.join(BIN, name)
         if not force and newer(exe, ours + objs + [os.path.realpath(os.path.join(STAGE, src))]):
             return name, "up to date"
-        run([NVCC, *fl, *extra, os.path.join(STAGE, src), *objs, *link_flags, "-o", exe], f"build {name}")
+        use = [objs[0], launcher_cublas] if "-DJZ_LEGACY_CUBLAS_HANDLE" in extra else objs
+        run([NVCC, *fl, *extra, os.path.join(STAGE, src), *use, *link_flags, "-o", exe], f"build {name}")
         return name, "built"
 
     todo = [p for p in PROGRAMS + [(n, "tests/" + s, []) for n, s in OWN_TESTS] if not only or p[0] in only]

@@ -44,6 +44,15 @@ bool lazy_enabled() {
 Storage::Storage(size_t n) : ptr(reinterpret_cast<float*>(Memory<CUDAfloat>::allocate(n))), count(n) {}
 Storage::~Storage() { Memory<CUDAfloat>::free(reinterpret_cast<CUDAfloat*>(ptr)); }
 
+// An unread product is LAUNCHED when the named matrix holding it is assigned over, so that timing loops of the form
+// `out = a * b` (tests/benchmarkCoreOps.cu:64-69, the CPU loop of examples/demo_gemm.cu) measure what they mean
+// to.  It is dropped only when it dies as a temporary or at scope exit -- e.g. the input gradient W^T*t of the first
+// layer, which backprop() returns and examples/demo_mnist.cu:120 discards.  Dead elementwise work, fills and draws
+// are always dropped: that is the point of deferring them.
+void Storage::retire_by_assignment() {
+    if (producer && producer->kind == Producer::GEMM && !producer->consumed) materialize();
+}
+
 bool Storage::lazy_ok() const { return lazy_enabled() && !escaped; }
 
 void add_reader(const StoragePtr& source, const StoragePtr& reader) {
@@ -250,6 +259,7 @@ Matrix<CUDAfloat>& Matrix<CUDAfloat>::operator=(const Matrix<CUDAfloat>& M) {
     if (this == &M) return *this;
     name = "copy of " + M.name;
     const float* from = M.dev();
+    if (elements && elements.use_count() == 1) store().retire_by_assignment();
     elements = new_storage(M.count());  // a fresh block, like the reference (cpp/cumatrix.cu:99-116)
     numrow = M.numrow;
     numcol = M.numcol;
@@ -260,6 +270,7 @@ Matrix<CUDAfloat>& Matrix<CUDAfloat>::operator=(const Matrix<CUDAfloat>& M) {
 
 Matrix<CUDAfloat>& Matrix<CUDAfloat>::operator=(Matrix<CUDAfloat>&& M) noexcept {
     if (this == &M) return *this;
+    if (elements && elements.use_count() == 1) store().retire_by_assignment();
     name = std::move(M.name);
     numrow = M.numrow;
     numcol = M.numcol;
@@ -399,6 +410,7 @@ bool Matrix<CUDAfloat>::add_broadcast(const Matrix<CUDAfloat>& B, float s1, floa
             vec->materialize();
             float* x = wdev();
             JZ_DO(jz_add_bcast(x, x, numrow, numcol, vec->ptr, dim, s1, s2, S()));
+            if (theirs->producer) theirs->producer->consumed = true;   // still defined (a later reader can run it)
             return true;
         }
     }

@@ -11,6 +11,9 @@
 //   * fills (the zero-init contract of the public constructor, ones()) and random draws are deferred too: a
 //     matrix that is constructed and then replaced or destroyed without being read -- every dummy weight,
 //     bias and Adam buffer of the per-iteration LogisticLayer in examples/demo_mnist.cu:118 -- costs no launch;
+//   * an unread deferred PRODUCT is launched when the named matrix holding it is assigned over (a benchmark loop
+//     `out = a * b` that never looks at `out` must still time the GEMM); it is dropped only when it dies as a
+//     temporary or at scope exit;
 //   * anything that needs real bytes (a read by a non-elementwise op, to_host, data(), printing)
 //     materialises: the whole program runs as ONE jz_chain pass, or as the epilogue of ONE jz_gemm_chain
 //     when the values come from a product whose un-materialised temporary has already died.
@@ -37,6 +40,7 @@ struct Producer {
     StoragePtr a, b;
     int ta = 0, tb = 0;
     size_t m = 0, n = 0, k = 0, lda = 0, ldb = 0;
+    bool consumed = false;   // its value already went into a fused pass (broadcast add): need not run if it dies unread
     // MAP: out[i] = steps(src[i]) over the flat physical buffer
     StoragePtr src;
     std::vector<jz_step> steps;
@@ -67,6 +71,7 @@ struct Storage {
     void flush_readers();           // deferred readers take their snapshot now
     void before_write();            // flush_readers + materialize: safe to modify the bytes in place
     void append(const jz_step& s);  // in-place elementwise step (deferred when allowed)
+    void retire_by_assignment();    // the owning matrix is being assigned over: launch an unread product (see cumatrix.cu)
     void define(std::unique_ptr<Producer> p);  // the WHOLE buffer is redefined (fill / random draw): old work is dropped
     float* escape();                // materialise for an outside reader/writer; disables deferral for good
 };

@@ -254,6 +254,18 @@ int compute() {
         check(max_abs_diff(keep(S5.to_host()), Ph + b * Matrix<float>::ones(1, 32)) < 1e-5f, "flagged operand takes the general path");
     }
 
+    // (14) a timing loop that never reads its result still runs one product per iteration (tests/benchmarkCoreOps.cu:64-69)
+    {
+        CM out("bench_gemm", n, n);
+        jz_sync(nullptr);
+        const unsigned long long before = jz_launch_count();
+        for (int i = 0; i < 5; i++) out = dA * dB;
+        const unsigned long long launches = jz_launch_count() - before;
+        std::cout << "    `out = a * b` x5 launches: " << launches << std::endl;
+        check(launches >= 4, "an unread product is launched when its variable is assigned over");
+        check(rel_fro(keep(out.to_host()), A * B) < 1e-5f, "and the last one is the product");
+    }
+
     const std::string path = std::string(PROJECT_DIR) + "/res/test_fusion_dump.bin";
     if (FILE* f = fopen(path.c_str(), "wb")) {
         for (const auto& m : dump) fwrite(m.data(), sizeof(float), m.num_row() * m.num_col(), f);

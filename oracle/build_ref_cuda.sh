@@ -21,4 +21,7 @@ for prog in demo_gemm demo_mnist; do
       -lcublas -lcurand "$OB" -Xlinker --disable-new-dtags -Xlinker -rpath -Xlinker "$(dirname "$OB")" -lpthread -o "$OUT/$prog" &
 done
 wait
+# the reference's operator benchmark (tests/benchmarkCoreOps.cu: GEMM 512^3, cuDNN conv, LayerNorm, attention block, Adam)
+[ "$OUT/benchmarkCoreOps" -nt "$OUT/cumatrix.o" ] || nvcc $FLAGS -DCUDNN_AVAILABLE "$REF/tests/benchmarkCoreOps.cu" "$OUT/launcher.o" "$OUT/cumatrix.o" "$OUT/cukernels.o" \
+    -lcublas -lcurand -lcudnn "$OB" -Xlinker --disable-new-dtags -Xlinker -rpath -Xlinker "$(dirname "$OB")" -lpthread -o "$OUT/benchmarkCoreOps"
 ls -la "$OUT" | grep -v "\.o$"

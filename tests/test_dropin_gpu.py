@@ -106,6 +106,25 @@ def test_demo_mnist_trains():
         assert min(errs[-3:]) < 0.2, f"MNIST test error did not drop: {errs[-5:]}"
 
 
+def test_reference_operator_benchmark_runs_unchanged():
+    """tests/benchmarkCoreOps.cu: GEMM, cuDNN ConvLayer, LayerNorm, TransformerLayer (its own kernels + cuBLAS batched GEMM
+    on global_handle) and adam_update on top of this backend's Matrix<CUDAfloat>.  Out-of-scope code paths: they must
+    keep working, and the GEMM row must time a real product (a deferred product assigned over is launched)."""
+    if not os.path.exists(os.path.join(BIN, "benchmarkCoreOps")):
+        pytest.skip("benchmarkCoreOps was not built (no cuDNN headers where the binaries were made)")
+    r = run("benchmarkCoreOps", timeout=600, env={"JUZHEN_BENCH_ITERS": "20"})
+    assert r.returncode == 0, r.stdout[-2000:]
+    import re
+    rows = {}
+    for ln in r.stdout.splitlines():
+        for op in ("GEMM", "Conv2D forward", "LayerNorm forward", "Attention block forward", "Adam update"):
+            m = re.match(re.escape(op) + r"\s+\S.*?\s+([0-9.]+)\s+([0-9.]+)\s+\S+\s*$", ln)
+            if m:
+                rows[op] = float(m.group(1))
+    assert len(rows) == 5, r.stdout[-2000:]
+    assert 0.003 < rows["GEMM"] < 1.0, rows      # 512^3 in 3xTF32: ~10-20 us, never 0
+
+
 def test_knn_runs():
     r = run("knn", timeout=1500)
     assert r.returncode == 0
