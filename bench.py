@@ -315,6 +315,9 @@ def run_ours(args):
 
     clk = clocks.stop() if rank == 0 else None   # sampled across every timed region above (sweep, per-op, e2e, GEMM)
     sharded = None
+    sharded_sum = None
+    if world > 1:
+        sharded_sum = run_sharded_colsum(jz, L, sw, world, stream, timed, pk)
     if world > 1 and not args.no_gemm:
         sharded = run_sharded_gemm(jz, L, args, world, rank, stream, timed, pk)
 
@@ -339,13 +342,35 @@ def run_ours(args):
                        "algorithmic_bytes_per_step": sw.bytes_per_step, "parallelism": f"independent shards x{world}"},
             "frac_of_hbm_peak": round(value / world / pk["hbm_gbs"], 3),
             "frac_of_8TBs_spec": round(value / world / 8000.0, 3),
-            "roofline": roofline, "ops": per_op, "gemm": gemm, "sharded_gemm": sharded, "mnist_step": mnist, "e2e": e2e,
+            "roofline": roofline, "ops": per_op, "gemm": gemm, "sharded_gemm": sharded, "sharded_colsum": sharded_sum, "mnist_step": mnist, "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sharded_colsum(jz, L, sw, world, stream, timed, pk):
+    """column sums of a matrix whose ROWS are sharded over the ranks (each rank holds rows/N x cols... here its
+    own 2^28-element shard, i.e. a (N*rows) x cols matrix in total): local jz_sum over the shard + ONE all-reduce of the
+    length-cols partial vector (NCCL over NVLink; NVLS in-switch reduction when available).  Weak scaling."""
+    import torch
+    from juzhen_b200 import mg
+    part = torch.empty(sw.cols, dtype=torch.float32, device="cuda")
+
+    def local_only():
+        jz._lib.check(L.jz_sum(part.data_ptr(), sw.X.ptr, sw.rows, sw.cols, sw.rows, 0, stream))
+
+    def with_allreduce():
+        local_only()
+        mg.allreduce_partial_sums(part)
+
+    ms_local, _ = timed(local_only, 10, 3)
+    ms_full, _ = timed(with_allreduce, 10, 3)
+    gbs = 4.0 * sw.n * world / (ms_full * 1e-3) / 1e9
+    return {"ms_local_sum": round(ms_local, 4), "ms_with_allreduce": round(ms_full, 4), "allreduce_bytes": 4 * sw.cols,
+            "GB/s_aggregate": round(gbs, 1), "frac_of_hbm_peak_xN": round(gbs / (pk["hbm_gbs"] * world), 3)}
 
 
 def run_sharded_gemm(jz, L, args, world, rank, stream, timed, pk):

@@ -45,6 +45,21 @@ def main():
             msgs.append(f"rank{rank} {m}x{n}x{k} {mode}: bit-exact={same}")
             ok &= same
             del g
+    # column sums over ROW-sharded data: local jz_sum + one all-reduce == the sum over the stacked matrix
+    rows, cols = 4096, 300
+    rng = np.random.default_rng(100 + rank)
+    Xr = np.asfortranarray(rng.standard_normal((rows, cols)).astype(np.float32))
+    x = jz.CM(Xr)
+    part = torch.empty(cols, dtype=torch.float32, device="cuda")
+    jz._lib.check(L.jz_sum(part.data_ptr(), x.ptr, rows, cols, rows, 0, stream))
+    mg.allreduce_partial_sums(part)
+    want = np.zeros(cols, dtype=np.float64)
+    for r in range(world):
+        want += np.random.default_rng(100 + r).standard_normal((rows, cols)).astype(np.float32).sum(axis=0, dtype=np.float64)
+    got = part.cpu().numpy().astype(np.float64)
+    same = bool(np.all(np.abs(got - want) <= 1e-5 * np.sqrt(rows * world) * 4))
+    msgs.append(f"rank{rank} row-sharded column sums + all-reduce: ok={same}")
+    ok &= same
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     print("\n".join(msgs), flush=True)
