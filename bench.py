@@ -511,10 +511,26 @@ def run_cpu(log2n, steps, warmup):
         step()
     dt = (time.perf_counter() - t0) / steps
     bytes_per_step = sum(b for _, b in SWEEP) * n
-    return {"value": round(bytes_per_step / dt / 1e9, 4), "unit": "GB/s", "cores": int(threads), "kind": kind,
-            "sample": f"one pass of the same {len(SWEEP)}-op sweep on 2^{log2n} elements "
-                      f"({dt:.2f} s/step; elementwise loops are single-threaded in the reference, "
-                      f"sum() uses OpenBLAS sgemv on {threads} threads)", "ms_per_step": round(dt * 1e3, 1)}
+    out = {"value": round(bytes_per_step / dt / 1e9, 4), "unit": "GB/s", "cores": int(threads), "kind": kind,
+           "sample": f"one pass of the same {len(SWEEP)}-op sweep on 2^{log2n} elements "
+                     f"({dt:.2f} s/step; elementwise loops are single-threaded in the reference, "
+                     f"sum() uses OpenBLAS sgemv on {threads} threads)", "ms_per_step": round(dt * 1e3, 1)}
+    if kind == "reference" and log2n >= 20:
+        # the GEMM half of the metric on the same host cores: the reference's Matrix<float>::dot (cblas_sgemm, OpenBLAS)
+        import numpy as np
+        import oracle
+        O = oracle.ref()
+        gn = 4096
+        rng = np.random.default_rng(1)
+        A = np.asfortranarray(rng.standard_normal((gn, gn), dtype=np.float32))
+        B = np.asfortranarray(rng.standard_normal((gn, gn), dtype=np.float32))
+        O.gemm(A[:512, :512], 0, B[:512, :512], 0)   # thread pool warm-up
+        t0 = time.perf_counter()
+        O.gemm(A, 0, B, 0)
+        g = time.perf_counter() - t0
+        out["gemm_4096"] = {"TFLOP/s": round(2.0 * gn ** 3 / g / 1e12, 3), "ms": round(g * 1e3, 1), "cores": int(threads),
+                            "what": "reference Matrix<float>::dot -> cblas_sgemm (OpenBLAS), one 4096^3 product"}
+    return out
 
 
 def cpu_reference_subprocess(log2n, steps, warmup=0):
