@@ -398,3 +398,33 @@ def test_large_flat_properties(jz, log2n):
     tot0 = float(jz.sum(jz.sum(v, 0), 1).to_host()[0, 0])
     tot1 = float(jz.sum(jz.sum(v, 1), 0).to_host()[0, 0])
     assert abs(tot0 - tot1) <= 1e-5 * np.sqrt(n) * 4 and abs(tot0 - s1) <= 1e-5 * np.sqrt(n) * 4
+
+
+def test_more_than_2_to_32_elements(jz):
+    """The reference casts element counts to unsigned int (cpp/cumatrix.cuh:59-62) and window indices to int
+    (cpp/cukernels.cu:79-83); here every index is size_t.  65536 x 65552 = 2^32 + 2^20 elements (16 GiB): fill, in-place
+    affine map, column and row sums with exactly representable results, a marker written past element 2^32, and a
+    transposing copy of the far corner."""
+    import torch
+    if torch.cuda.mem_get_info()[0] < 40 * (1 << 30):
+        pytest.skip("needs ~17 GiB of free device memory")
+    L = jz.lib()
+    rows, cols = 65536, 65552
+    n = rows * cols
+    assert n > (1 << 32)
+    x = jz.CM.empty("big", rows, cols)
+    jz._lib.check(L.jz_fill(x.ptr, n, 1.5, None))
+    jz._lib.check(L.jz_affine(x.ptr, x.ptr, n, 2.0, 1.0, None))                     # 4.0 everywhere
+    jz._lib.check(L.jz_fill(x.ptr + 4 * (n - 3), 3, 7.0, None))                       # marker in the last column
+    c = jz.CM.empty("c", cols, 1)
+    r = jz.CM.empty("r", rows, 1)
+    jz._lib.check(L.jz_sum(c.ptr, x.ptr, rows, cols, rows, 0, None))
+    jz._lib.check(L.jz_sum(r.ptr, x.ptr, rows, cols, rows, 1, None))
+    cs, rs = c.to_host().ravel(), r.to_host().ravel()
+    assert np.all(cs[:-1] == 4.0 * rows) and cs[-1] == 4.0 * rows + 3 * 3.0
+    assert np.all(rs[:-3] == 4.0 * cols) and np.all(rs[-3:] == 4.0 * cols + 3.0)
+    # far corner through the 2-D window path: last 4 rows x last 2 columns, transposed
+    w = jz.CM.empty("w", 2, 4)
+    off = (cols - 2) * rows + (rows - 4)
+    jz._lib.check(L.jz_copy2d(w.ptr, 2, x.ptr + 4 * off, rows, 2, 4, 1, None))
+    assert np.array_equal(w.to_host(), np.array([[4, 4, 4, 4], [4, 7, 7, 7]], dtype=np.float32))
