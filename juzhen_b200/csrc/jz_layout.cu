@@ -298,7 +298,11 @@ int jz_copy2d(float* dst, size_t ldd, const float* src, size_t lds, size_t rows,
     }
     if (aligned16(dst) && aligned16(src) && ldd % 4 == 0 && lds % 4 == 0 && rows >= 64 && cols >= 64) {
         const size_t t64_i = ceil_div(rows, size_t(64)), t64_j = ceil_div(cols, size_t(64));
-        JZ_LAUNCH(transpose64_kernel, tile_grid(t64_i * t64_j), 256, 0, s, dst, ldd, src, lds, rows, cols, t64_i, t64_j);
+        // one tile per CTA (the hardware scheduler keeps every SM's queue of loads full): measured 6.51 TB/s against 6.06
+        // for the best persistent grid (profiles/r01h_tune_transpose.log)
+        const size_t nt = t64_i * t64_j;
+        const unsigned grid = unsigned(nt < 0x7fffffffull ? nt : 0x7fffffffull);
+        JZ_LAUNCH(transpose64_kernel, grid, 256, 0, s, dst, ldd, src, lds, rows, cols, t64_i, t64_j);
         return JZ_OK;
     }
     const size_t tiles_i = ceil_div(rows, kTile), tiles_j = ceil_div(cols, kTile);
