@@ -147,3 +147,48 @@ def test_gemm_4096_sampled_block_vs_oracle(jz, port):
         jz._lib.check(jz.lib().jz_copy2d(at.ptr, n, a.ptr, n, n, n, 1, None))
         c2 = at.T().dot(b, mode=mode)
         assert rel_fro(c2.columns(1000, 1064).to_host(), truth) < tol
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_gemm_fuzz_shapes_offsets_strides(jz, seed):
+    """dispatch boundaries (small-product / tensor / SIMT / rank-1 / k = 0), all flag combinations, leading dimensions
+    with padding, base pointers that are not 16-byte aligned, alpha/beta: 25 random cases per seed against float64"""
+    rng = np.random.default_rng(1000 + seed)
+    L = jz.lib()
+    for case in range(25):
+        big = rng.random() < 0.3
+        hi = 700 if big else 90
+        m, n = int(rng.integers(1, hi)), int(rng.integers(1, hi))
+        k = int(rng.integers(0, hi))
+        ta, tb = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        pa, pb, pc = (int(rng.integers(0, 6)) for _ in range(3))         # ld padding
+        oa, ob, oc = (int(rng.integers(0, 4)) for _ in range(3))         # base offsets in floats
+        ar, ac = (k, m) if ta else (m, k)
+        br, bc = (n, k) if tb else (k, n)
+        lda, ldb, ldc = max(ar, 1) + pa, max(br, 1) + pb, m + pc
+        A = rng.standard_normal(oa + lda * max(ac, 1)).astype(np.float32)
+        B = rng.standard_normal(ob + ldb * max(bc, 1)).astype(np.float32)
+        C0 = rng.standard_normal(oc + ldc * n).astype(np.float32)
+        alpha = float(rng.choice([1.0, -0.5, 2.0]))
+        beta = float(rng.choice([0.0, 0.0, 1.0, -0.25]))
+        dA = jz.CM(np.asfortranarray(A.reshape(-1, 1)))
+        dB = jz.CM(np.asfortranarray(B.reshape(-1, 1)))
+        dC = jz.CM(np.asfortranarray(C0.reshape(-1, 1)))
+        mode = int(rng.choice([0, 0, 1, 2]))
+        jz._lib.check(L.jz_gemm(ta, tb, m, n, k, alpha, dA.ptr + 4 * oa, lda, dB.ptr + 4 * ob, ldb, beta, dC.ptr + 4 * oc, ldc, mode, None))
+        got = dC.to_host().ravel()
+        Am = A[oa:oa + lda * ac].reshape(lda, ac, order="F")[:ar, :].astype(np.float64) if ac else np.zeros((ar, 0))
+        Bm = B[ob:ob + ldb * bc].reshape(ldb, bc, order="F")[:br, :].astype(np.float64) if bc else np.zeros((br, 0))
+        opA = Am.T if ta else Am
+        opB = Bm.T if tb else Bm
+        Cm = C0[oc:oc + ldc * n].reshape(ldc, n, order="F").astype(np.float64)
+        want = Cm.copy()
+        want[:m, :] = alpha * (opA @ opB) + beta * Cm[:m, :]
+        gotm = got[oc:oc + ldc * n].reshape(ldc, n, order="F")
+        tol = 1e-3 if mode == 1 else 1e-5
+        scale = np.abs(alpha) * (np.abs(opA) @ np.abs(opB)) + np.abs(beta * Cm[:m, :]) + 1e-30
+        desc = (seed, case, m, n, k, ta, tb, lda, ldb, ldc, oa, ob, oc, alpha, beta, mode, L.jz_gemm_last_path())
+        assert np.all(np.abs(gotm[:m, :] - want[:m, :]) <= tol * scale * 4 + 1e-6), desc
+        # nothing outside the m x n window moved: padding rows, and the floats in front of the base pointer
+        assert np.array_equal(gotm[m:, :], Cm[m:, :].astype(np.float32)), desc
+        assert np.array_equal(got[:oc], C0[:oc]), desc
