@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -264,6 +265,43 @@ int compute() {
         std::cout << "    `out = a * b` x5 launches: " << launches << std::endl;
         check(launches >= 4, "an unread product is launched when its variable is assigned over");
         check(rel_fro(keep(out.to_host()), A * B) < 1e-5f, "and the last one is the product");
+    }
+
+    // (15) random programs over a pool of matrices: every aliasing pattern the API allows (source == destination, T()
+    //      views of the destination, copies taken before a source changes, rvalue chains, products feeding chains,
+    //      broadcast idioms, refills).  The dump of this section must be bit-identical between the deferred and the
+    //      eager (JZ_EAGER=1) run -- tests/test_dropin_gpu.py compares them -- and finite.
+    {
+        std::mt19937 rng(20261017);
+        const size_t d = 48;
+        std::vector<CM> pool;
+        for (int i = 0; i < 6; i++) pool.emplace_back(CM(Matrix<float>::randn(d, d)));
+        bool finite = true;
+        for (int step = 0; step < 400; step++) {
+            const int op = rng() % 14, i = rng() % 6, j = rng() % 6, k = rng() % 6;
+            switch (op) {
+                case 0: pool[k] = tanh(pool[i]); break;
+                case 1: pool[k] = tanh(std::move(pool[k]) * 0.5f + 0.1f); break;
+                case 2: pool[k] = tanh(pool[i] + pool[j]); break;
+                case 3: pool[k] = tanh(pool[i] - pool[j] * 0.5f); break;
+                case 4: pool[k] = hadmd(pool[i], pool[j]); break;
+                case 5: pool[k] = tanh(pool[i] * pool[j] / (float)d); break;
+                case 6: pool[k] = tanh(pool[i].T() * pool[j] / (float)d + 0.05f); break;
+                case 7: pool[k] += pool[i]; pool[k] = tanh(std::move(pool[k])); break;
+                case 8: pool[k] = exp(-square(pool[i])); break;
+                case 9: pool[k] = tanh(pool[i].T() + pool[j]); break;
+                case 10: pool[k].zeros(); pool[k] += pool[i]; break;
+                case 11: pool[k] = tanh(CM::ones(d, d) * 0.25f + pool[i] * pool[j].T() / (float)d); break;
+                case 12: { CM t = pool[i]; pool[i] = tanh(std::move(pool[i]) * 1.5f); pool[k] = t - pool[i]; pool[k] = tanh(std::move(pool[k])); break; }
+                default: pool[k] = tanh(pool[i] - CM::ones(d, 1) * sum(pool[i], 0) / (float)d); break;
+            }
+            if (step % 20 == 19) {
+                Matrix<float> h = keep(pool[rng() % 6].to_host());
+                for (size_t c = 0; c < d; c++) for (size_t r = 0; r < d; r++) finite &= std::isfinite(h.elem(r, c));
+            }
+        }
+        for (auto& m : pool) keep(m.to_host());
+        check(finite, "400-step random program stays finite (dump compared bitwise against the eager run)");
     }
 
     const std::string path = std::string(PROJECT_DIR) + "/res/test_fusion_dump.bin";
