@@ -989,7 +989,11 @@ static int gemm_local(int ta, int tb, size_t m, size_t n, size_t k, float alpha,
         return JZ_OK;
     }
     const bool want_tc = (mode == JZ_GEMM_3XTF32 || mode == JZ_GEMM_TF32 || mode == JZ_GEMM_BF16) && ctx().cc_major == 10;
-    const bool big_enough = m >= 64 && n >= 64 && k >= 32 && (double(m) * double(n) * double(k) >= double(1 << 22));
+    // tensor path: a reasonably filled tile grid (m, n >= 64, k >= 32) from 2^22 multiply-adds up, and EVERY product
+    // beyond the small-product kernel's range (2^26): skinny ones too -- a 4096 x 4096 x 48 product wastes most of its
+    // 256-wide tiles and is still an order of magnitude faster there than on the fp32 SIMT kernel
+    const double macs = double(m) * double(n) * double(k);
+    const bool big_enough = (m >= 64 && n >= 64 && k >= 32 && macs >= double(1 << 22)) || macs > double(1 << 26);
     const bool fits_i32 = m < (size_t(1) << 31) && n < (size_t(1) << 31) && k < (size_t(1) << 31);
     static const bool force_simt = std::getenv("JZ_GEMM_FORCE_SIMT") != nullptr;
     if (want_tc && big_enough && fits_i32 && !force_simt) {

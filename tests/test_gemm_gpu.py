@@ -48,7 +48,7 @@ def test_gemm_shape_error(jz):
 
 @pytest.mark.parametrize("mode", ["3xtf32", "tf32", "fp32"])
 @pytest.mark.parametrize("shape", [(256, 256, 256), (384, 300, 520), (130, 1000, 70), (640, 320, 384), (1024, 512, 768),
-                                   (515, 2049, 257)])
+                                   (515, 2049, 257), (2048, 2048, 48), (20, 3000, 3000), (3000, 40, 3000)])
 def test_gemm_all_flags_vs_oracle(jz, port, mode, shape):
     m, k, n = shape
     rng = np.random.default_rng(m * 7 + k * 3 + n)
@@ -62,7 +62,7 @@ def test_gemm_all_flags_vs_oracle(jz, port, mode, shape):
             path = jz.lib().jz_gemm_last_path()
             print(f"gemm {mode} {shape} ta={ta} tb={tb}: rel_fro={err:.3e} path={path}")
             assert err < TOL[mode], (mode, shape, ta, tb, err)
-            if mode != "fp32" and min(m, n) >= 64 and m * n * k >= (1 << 22):
+            if mode != "fp32" and ((min(m, n) >= 64 and m * n * k >= (1 << 22)) or m * n * k > (1 << 26)):
                 assert path == 1, "expected the tcgen05 kernel"
             elif m * n * k <= (1 << 26):
                 assert path == 4, "expected the small-product kernel"
