@@ -16,7 +16,7 @@ for unit in launcher cumatrix cukernels; do
   [ "$OUT/$unit.o" -nt "$REF/cpp/$unit.cu" ] || nvcc $FLAGS -c "$REF/cpp/$unit.cu" -o "$OUT/$unit.o" &
 done
 wait
-for prog in demo_gemm demo_mnist; do
+for prog in demo_gemm demo_mnist demo_classification helloworld_nn knn; do
   [ "$OUT/$prog" -nt "$OUT/cumatrix.o" ] || nvcc $FLAGS "$REF/examples/$prog.cu" "$OUT/launcher.o" "$OUT/cumatrix.o" "$OUT/cukernels.o" \
       -lcublas -lcurand "$OB" -Xlinker --disable-new-dtags -Xlinker -rpath -Xlinker "$(dirname "$OB")" -lpthread -o "$OUT/$prog" &
 done
