@@ -53,7 +53,7 @@ PROGRAMS = [
     ("benchmarkCoreOps", "tests/benchmarkCoreOps.cu", ["-DCUDNN_AVAILABLE", "-DJZ_LEGACY_CUBLAS_HANDLE", "-lcudnn", "-lcublas"]),
 ]
 # this repository's own C++ tests (same compute() convention), staged next to the reference's tests
-OWN_TESTS = [("test_fusion", "test_fusion.cu"), ("bench_attention", "bench_attention.cu")]
+OWN_TESTS = [("test_fusion", "test_fusion.cu"), ("bench_attention", "bench_attention.cu"), ("bench_overhead", "bench_overhead.cu")]
 OURS_IN_CPP = {"cumatrix.cuh", "memory.hpp", "jz_lazy.hpp"}
 REF_CPP = ["core.hpp", "matrix.hpp", "operators.hpp", "helper.hpp", "juzhen.hpp", "cpulinalg.hpp"]
 
