@@ -661,6 +661,113 @@ static int reduce_entry(float* out, const float* a, size_t rows, size_t cols, si
     return dim == 0 ? reduce_dim0<Op>(out, a, rows, cols, ld, s) : reduce_dim1<Op>(out, a, rows, cols, ld, s);
 }
 
+// Columns too long for one CTA's registers: the CL CTAs of a thread-block cluster hold one column between them (512
+// threads x NV float4 each), exchange their partial max and partial sum through distributed shared memory, and the
+// column is still read once and written once (rows > 32768 used to fall back to the three-pass warp kernel, 20 B per
+// element).  Up to 32768 rows one 512-thread CTA per column stays faster: two cluster barriers per column cost more
+// than they save there (measured at 32768^2: 0.75 against 0.80 of the copy peak).
+template <int NV, int CL>
+__global__ void __launch_bounds__(512)
+softmax_cluster_kernel(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode, float rnb) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float red[16];
+    __shared__ float xchg[2];   // this CTA's partial max / partial sum, read by the other CTAs of the cluster
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned r = cluster.block_rank();
+    const size_t n4 = rows >> 2;
+    const size_t seg = (n4 + CL - 1) / CL;                  // float4 words per CTA
+    const size_t lo = size_t(r) * seg, hi = lo + seg < n4 ? lo + seg : n4;
+    const size_t ncl = gridDim.x / CL;
+    for (size_t c = blockIdx.x / CL; c < cols; c += ncl) {
+        const float4* col = reinterpret_cast<const float4*>(a + c * ld);
+        float4 v[NV];
+        float m = -1e30f;
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const size_t i = lo + threadIdx.x + size_t(q) * 512;
+            if (i < hi) {
+                v[q] = col[i];
+                m = fmaxf(m, fmaxf(fmaxf(v[q].x, v[q].y), fmaxf(v[q].z, v[q].w)));
+            }
+        }
+        m = warp_reduce<MaxOp>(m);
+        if (lane == 0) red[warp] = m;
+        __syncthreads();
+        m = warp_reduce<MaxOp>(red[lane & 15]);
+        if (threadIdx.x == 0) xchg[0] = m;
+        cluster.sync();
+#pragma unroll
+        for (int q = 0; q < CL; q++) m = fmaxf(m, cluster.map_shared_rank(xchg, q)[0]);
+        float z = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const size_t i = lo + threadIdx.x + size_t(q) * 512;
+            if (i < hi) {
+                v[q].x = expf(__fadd_rn(-m, v[q].x)); v[q].y = expf(__fadd_rn(-m, v[q].y));
+                v[q].z = expf(__fadd_rn(-m, v[q].z)); v[q].w = expf(__fadd_rn(-m, v[q].w));
+                z += (v[q].x + v[q].y) + (v[q].z + v[q].w);
+            }
+        }
+        z = warp_reduce<SumOp>(z);
+        __syncthreads();   // `red` readers of the max are done
+        if (lane == 0) red[warp] = z;
+        __syncthreads();
+        z = red[lane & 15];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+        if (threadIdx.x == 0) xchg[1] = z;
+        cluster.sync();
+        z = 0.0f;
+#pragma unroll
+        for (int q = 0; q < CL; q++) z += cluster.map_shared_rank(xchg, q)[1];   // same order in every CTA
+        const float inv = __fdiv_rn(1.0f, z);
+        float4* o4 = reinterpret_cast<float4*>(out + c * rows);
+        const float4* y4 = reinterpret_cast<const float4*>(mode == 1 ? y + c * rows : nullptr);
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const size_t i = lo + threadIdx.x + size_t(q) * 512;
+            if (i < hi) {
+                float4 t;
+                t.x = __fmul_rn(v[q].x, inv); t.y = __fmul_rn(v[q].y, inv);
+                t.z = __fmul_rn(v[q].z, inv); t.w = __fmul_rn(v[q].w, inv);
+                if (mode == 1) {
+                    const float4 u = y4[i];
+                    t.x = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-t.x, u.x), 0.0f)), 0.0f);
+                    t.y = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-t.y, u.y), 0.0f)), 0.0f);
+                    t.z = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-t.z, u.z), 0.0f)), 0.0f);
+                    t.w = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-t.w, u.w), 0.0f)), 0.0f);
+                }
+                o4[i] = t;
+            }
+        }
+        cluster.sync();   // nobody overwrites xchg for the next column while a peer may still read it
+    }
+}
+
+template <int NV, int CL>
+static int launch_softmax_cluster(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode,
+                                  float rnb, cudaStream_t s) {
+    const size_t slots = size_t(ctx().sm_count) * 2 / CL;   // ~2 CTAs per SM
+    const size_t ncl = cols < slots ? cols : slots;
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(unsigned(ncl * CL), 1, 1);
+    cfg.blockDim = dim3(512, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, softmax_cluster_kernel<NV, CL>, out, a, y, rows, cols, ld, mode, rnb);
+    ctx().launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return cuda_fail(e, "softmax_cluster_kernel launch");
+    return JZ_OK;
+}
+
 }  // namespace jz
 
 using namespace jz;
@@ -692,7 +799,16 @@ static int softmax_impl(float* out, const float* a, const float* y, size_t rows,
         return JZ_OK;
     }
     const bool vec = aligned16(a) && ld % 4 == 0;
-    const bool regs_ok = vec && rows % 4 == 0 && aligned16(out) && (mode == 0 || aligned16(y)) && rows <= 32768;
+    const bool regs_base = vec && rows % 4 == 0 && aligned16(out) && (mode == 0 || aligned16(y));
+    static const bool no_cluster_sm = std::getenv("JZ_SOFTMAX_NO_CLUSTER") != nullptr;
+    if (regs_base && rows > 32768 && rows <= 262144 && !no_cluster_sm) {   // column shared by a cluster (see the kernel)
+        const size_t n4 = rows >> 2;
+        if (n4 <= 8192) return launch_softmax_cluster<8, 2>(out, a, y, rows, cols, ld, mode, rnb, s);
+        if (n4 <= 16384) return launch_softmax_cluster<8, 4>(out, a, y, rows, cols, ld, mode, rnb, s);
+        if (n4 <= 32768) return launch_softmax_cluster<8, 8>(out, a, y, rows, cols, ld, mode, rnb, s);
+        return launch_softmax_cluster<16, 8>(out, a, y, rows, cols, ld, mode, rnb, s);
+    }
+    const bool regs_ok = regs_base && rows <= 32768;
     if (regs_ok) {
         const size_t n4 = rows >> 2;
         if (n4 <= 512) {  // one warp per column

@@ -215,6 +215,29 @@ def test_softmax_head_vs_reference_fixture(jz, golden):
     assert np.allclose(got2.sum(axis=0), 1.0, atol=1e-5)
 
 
+@pytest.mark.parametrize("rows", [16388, 20000, 32768, 40000, 70000, 131076, 200000, 262144, 300000])
+def test_softmax_long_columns_cluster(jz, port, rows):
+    """columns shared by a thread-block cluster (2 / 4 / 8 CTAs exchanging max and sum through distributed shared
+    memory) up to 262144 rows; beyond that the three-pass fallback; both modes (plain softmax, CE gradient)"""
+    rng = np.random.default_rng(rows)
+    cols = 37
+    X = F(rng.standard_normal((rows, cols)) * 3)
+    # truth in float64: the oracle's sequential fp32 sum over > 16384 terms is itself ~1e-5 off
+    X64 = X.astype(np.float64)
+    E = np.exp(X64 - X64.max(axis=0, keepdims=True))
+    ref = E / E.sum(axis=0, keepdims=True)
+    got = jz.softmax_cols(jz.CM(X)).to_host()
+    assert np.all(np.abs(got - ref) <= 1e-5 * np.abs(ref) + 1e-30)
+    assert np.all(np.abs(port.softmax_cols(X) - ref) <= 5e-3 * np.abs(ref) + 1e-30)      # the oracle (sequential fp32 sum, as the reference) agrees to ITS accuracy
+    assert np.allclose(got.sum(axis=0, dtype=np.float64), 1.0, atol=1e-5)
+    assert same_bits(jz.softmax_cols(jz.CM(X)).to_host(), got)            # deterministic
+    if rows in (20000, 70000):
+        Y = F((rng.random((rows, cols)) < 1e-4).astype(np.float32))
+        g = jz.softmax_ce_grad(jz.CM(X), jz.CM(Y), 32).to_host()
+        refg = -(Y.astype(np.float64) - ref) / 32.0
+        assert np.all(np.abs(g - refg) <= 1e-5 * np.abs(refg) + 1e-9)
+
+
 def test_softmax_composite_through_operators(jz, golden):
     """the reference's own formulation (ml/layer.hpp:254-262) through the mirrored operators,
     including the rank-1 GEMM broadcasts, equals the fused kernel."""
