@@ -15,8 +15,10 @@
 //     summed in a fixed order -> deterministic results;
 //   * narrow column blocks keep the grid at >= one CTA per SM for the shapes that matter; A is re-read from L2
 //     by the CTAs that share a row block.
-// Measured on B200 inside a launch loop (scripts/small_gemm_bench.py, warm L2): (1024 x 784)(784 x 32) 51 -> 10 us,
-// (128 x 1024)(1024 x 32) 71 -> 12 us, (1024 x 784)^T(1024 x 32) 72 -> 16 us against the shared-memory-tiled kernel.
+// Measured on B200 inside a launch loop (scripts/small_gemm_bench.py, warm L2): (1024 x 784)(784 x 32) 51 -> 9 us,
+// (128 x 1024)(1024 x 32) 71 -> 10 us, (1024 x 784)^T(1024 x 32) 72 -> 14 us against the shared-memory-tiled kernel.
+// ncu with a warm cache: 10 us, 1.96 instructions per cycle per SM, a third of the stalls on the shuffle (MIO) queue --
+// what is left is instruction issue (32 shuffles per 32 FMAs), not memory latency.
 // Products with m, n >= 64 and k >= 32 stay on the tensor-core path (8 us at (1024 x 32)(32 x 784)).
 // alpha/beta and the fused elementwise chain are applied exactly as in the other GEMM kernels.
 #include "jz_common.cuh"
