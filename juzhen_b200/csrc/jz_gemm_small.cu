@@ -44,10 +44,11 @@ __device__ __forceinline__ void sk_load_a(float (&a)[4], const float* __restrict
 
 // The 4 k x 8 columns of op(B) one iteration needs are exactly one float per lane: each lane loads ONE element
 // (plain B: lane = 4*j + q reads B[(j0+j)*ldb + kk + q], eight 16-byte runs; flagged B: lane = 8*q + j reads
-// B[(kk+q)*ldb + j0 + j], four 32-byte runs) and the warp shares them by shuffle.  One load instruction per
-// iteration instead of eight warp-uniform 128-bit loads, and one live register instead of 32: with 4 A loads that
-// is 5 loads per iteration, so several iterations' loads fit in flight even under the 64-register budget of a
-// 1024-thread CTA (the uniform-load form interleaved its loads with the FMAs and paid ~5 round trips per iteration).
+// B[(kk+q)*ldb + j0 + j], four 32-byte runs), parks it in a 128-byte warp-private shared-memory line, and every lane
+// reads the line back as eight broadcast 128-bit words {B(kk..kk+3, j)}.  One global load instruction per iteration
+// instead of eight warp-uniform ones, one live register instead of 32 (several iterations' loads fit in flight under
+// the 64-register budget of a 1024-thread CTA), and 9 shared-memory instructions instead of the 32 shuffles of the
+// register-only form, which left the kernel issue-bound on the shuffle queue (ncu: a third of all stalls).
 template <bool TB, int NT>
 __device__ __forceinline__ float sk_load_b(const float* __restrict__ B, size_t ldb, size_t kk, size_t j0, size_t n, int lane) {
     static_assert(NT == 8, "one B element per lane: 4 k x 8 columns");
@@ -55,12 +56,19 @@ __device__ __forceinline__ float sk_load_b(const float* __restrict__ B, size_t l
     const size_t jj = j0 + j < n ? j0 + j : n - 1;   // clamped: surplus columns are computed, never stored
     return TB ? B[(kk + q) * ldb + jj] : B[jj * ldb + kk + q];
 }
+// line: this warp's 32-float buffer for this iteration (double-buffered by the caller); slot j*4 + q holds B(kk+q, j)
 template <bool TB, int NT>
-__device__ __forceinline__ void sk_fma_b(float (&acc)[NT], const float (&a)[4], float bval) {
+__device__ __forceinline__ void sk_fma_b(float (&acc)[NT], const float (&a)[4], float bval, float* line, int lane) {
+    line[TB ? ((lane & 7) << 2) + (lane >> 3) : lane] = bval;
+    __syncwarp();
 #pragma unroll
-    for (int j = 0; j < NT; j++)
-#pragma unroll
-        for (int q = 0; q < 4; q++) acc[j] = fmaf(a[q], __shfl_sync(0xffffffffu, bval, TB ? 8 * q + j : 4 * j + q), acc[j]);
+    for (int j = 0; j < NT; j++) {
+        const float4 b = reinterpret_cast<const float4*>(line)[j];
+        acc[j] = fmaf(a[0], b.x, acc[j]);
+        acc[j] = fmaf(a[1], b.y, acc[j]);
+        acc[j] = fmaf(a[2], b.z, acc[j]);
+        acc[j] = fmaf(a[3], b.w, acc[j]);
+    }
 }
 
 // KSPLIT: the CTA's warps split k (true) or take different column blocks (false).
@@ -72,6 +80,7 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
                                                                    size_t strideA, size_t strideB, size_t strideC) {
     __shared__ ChainParams chain;
     __shared__ float red[KSPLIT ? SK_WARPS : 1][KSPLIT ? NT : 1][32];
+    __shared__ __align__(16) float bline[SK_WARPS][2][32];   // per warp, two iterations deep
     stage_chain(&chain, chain_p, threadIdx.x);
     A += size_t(blockIdx.z) * strideA;   // strided batch (blockIdx.z = 0 for a single product)
     B += size_t(blockIdx.z) * strideB;
@@ -91,12 +100,14 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
     for (int j = 0; j < NT; j++) acc[j] = 0.0f;
     if (KSPLIT || j0 < n) {
         size_t kk = kbeg;
+        unsigned par = 0;
 #pragma unroll 4
         for (; kk + 4 <= kend; kk += 4) {
             float a[4];
             sk_load_a<TA, VEC>(a, A, lda, il, kk);
             const float bval = sk_load_b<TB, NT>(B, ldb, kk, j0, n, lane);
-            sk_fma_b<TB, NT>(acc, a, bval);
+            sk_fma_b<TB, NT>(acc, a, bval, bline[warp][par], lane);
+            par ^= 1u;
         }
         for (; kk < kend; kk++) {   // k tail, one at a time
             const float a = TA ? A[il * lda + kk] : A[kk * lda + il];
