@@ -576,7 +576,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2N_DEFAULT)
     ap.add_argument("--cpu-log2n", type=int, default=24, dest="cpu_log2n")
-    ap.add_argument("--gemm-n", type=int, nargs="*", default=[4096, 8192], dest="gemm_n")
+    ap.add_argument("--gemm-n", type=int, nargs="*", default=[2048, 4096, 8192, 16384], dest="gemm_n")
     ap.add_argument("--sharded-n", type=int, nargs="*", default=[16384, 32768], dest="sharded_n")
     ap.add_argument("--no-gemm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
