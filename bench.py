@@ -409,6 +409,30 @@ def run_sharded_gemm(jz, L, args, world, rank, stream, timed, pk):
             torch.cuda.empty_cache()
         if len(sums) == 2:
             res["fused_equals_nccl_bitwise"] = sums["nccl"] == sums["fused"]
+        # truth check at full size: 64 entries of this rank's column block recomputed in float64 on the device
+        try:
+            gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+            ii = torch.randint(0, n, (64,), generator=gen).cuda()
+            jj = torch.randint(j0, j1, (64,), generator=gen).cuda()
+            A2 = torch.empty(n * n, dtype=torch.float32, device="cuda")
+            L.jz_copy(A2.data_ptr(), a.ptr, n * n, stream)
+            B2 = torch.empty(n * (j1 - j0), dtype=torch.float32, device="cuda")
+            L.jz_copy(B2.data_ptr(), b.ptr, n * (j1 - j0), stream)
+            Arows = A2.view(n, n).t()[ii, :].double()                    # logical A[i, :] of the column-major buffer
+            Bcols = B2.view(j1 - j0, n)[jj - j0, :].double()             # logical B[:, j]
+            x = (Arows * Bcols).sum(dim=1) / n
+            want = torch.log(torch.exp(x) + 1.0) / 5.0
+            g2 = mg.GpuShardedGemm(jz, n, n, n, steps=steps, gemm_mode=0, mode="nccl")
+            cf = g2.run(a.ptr, n, 0, b.ptr, n, stream)
+            got = cf.view(n, n).t()[ii, jj].double()
+            rel = float((got - want).norm() / want.norm())
+            worst = torch.tensor([rel], device="cuda", dtype=torch.float64)
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            res["rel_err_64_sampled_entries_per_rank_vs_float64"] = float(f"{worst.item():.3e}")
+            del A2, B2, g2, cf
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            res["sampled_check_error"] = f"{type(e).__name__}: {e}"[:200]
         out[str(n)] = res
         del a, b
     return out
