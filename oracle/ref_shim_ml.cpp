@@ -1,0 +1,59 @@
+// oracle/ref_shim_ml.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Second shim over the UNMODIFIED reference headers, this one over ml/layer.hpp: the reference's own CPU formulation
+// (generic Matrix<float> operators) of the transformer helpers whose CUDA kernels the jz_* entry points of SURVEY row
+// 8f-3 replace -- row_softmax (ml/layer.hpp:2344-2367) and LayerNorm<float>::forward / backward (:2572-2700).
+// Used to pin oracle/jz_oracle.c's restatements of the CUDA kernels (jzo_softmax_rows_batched, jzo_layernorm_*) against
+// what the reference itself computes on the CPU, and to generate tests/golden/ref_ml_golden.npz.
+// Built by `make -C oracle ref-ml` into oracle/_ref/libjzref_ml.so (git-ignored).
+#include "cpp/juzhen.hpp"
+#include "ml/layer.hpp"
+
+int compute() { return 0; }
+
+namespace {
+using MF = Matrix<float>;
+MF owned(const float* p, size_t numrow, size_t numcol) {   // a copy the reference code may keep or move from
+    MF m("in", numrow, numcol);
+    std::memcpy((void*)m.data(), p, numrow * numcol * sizeof(float));
+    return m;
+}
+void emit(const MF& r, float* out) {
+    const size_t R = r.num_row(), C = r.num_col();
+    for (size_t j = 0; j < C; j++)
+        for (size_t i = 0; i < R; i++) out[j * R + i] = r.elem(i, j);
+}
+}  // namespace
+
+extern "C" {
+
+int refml_version() { return 1; }
+
+// one seq x seq block: out(a, :) = softmax over keys of x(a, :)
+int refml_row_softmax(const float* x, size_t rows, size_t cols, float* out) {
+    emit(Juzhen::row_softmax(owned(x, rows, cols)), out);
+    return 0;
+}
+
+int refml_layernorm_forward(const float* x, const float* gamma, const float* beta, size_t dim, size_t N, float* y,
+                            float* xhat, float* inv_std) {
+    Juzhen::LayerNorm<float> ln((int)dim, (int)N);
+    ln.gamma = owned(gamma, dim, 1);
+    ln.beta = owned(beta, dim, 1);
+    emit(ln.forward(owned(x, dim, N)), y);
+    emit(ln.cached_xhat, xhat);
+    emit(ln.cached_inv, inv_std);
+    return 0;
+}
+
+int refml_layernorm_backward(const float* dy, const float* gamma, const float* xhat, const float* inv_std, size_t dim,
+                             size_t N, float* dx) {
+    Juzhen::LayerNorm<float> ln((int)dim, (int)N);
+    ln.gamma = owned(gamma, dim, 1);
+    ln.cached_xhat = owned(xhat, dim, N);
+    ln.cached_inv = owned(inv_std, 1, N);
+    emit(ln.backward(owned(dy, dim, N), /*update=*/false), dx);
+    return 0;
+}
+
+}  // extern "C"

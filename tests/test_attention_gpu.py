@@ -45,6 +45,32 @@ def test_softmax_rows_batched(jz, port, S, batch, causal):
         assert np.array_equal(m, ref)
 
 
+def test_against_the_reference_cpu_formulation(jz):
+    """golden vectors from the UNMODIFIED reference's CPU formulation (row_softmax, LayerNorm<float>; tests/golden/
+    ref_ml_golden.npz, scripts/make_golden_ml.py): the jz_* kernels agree to 1e-5 relative"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ml_golden.npz"))
+    L = jz.lib()
+    for S in (7, 64, 130):
+        x = jz.CM(np.asfortranarray(g[f"sm_x_{S}"]))
+        y = jz.CM.empty("y", S, S)
+        jz._lib.check(L.jz_softmax_rows_batched(y.ptr, x.ptr, S, 1, 0, 0.0, None))
+        want = g[f"sm_y_{S}"]
+        assert np.all(np.abs(y.to_host() - want) <= 1e-5 * np.abs(want) + 1e-12)
+    for k in ("5x7", "64x33", "300x12"):
+        dim, N = (int(v) for v in k.split("x"))
+        xm, gm, bm = jz.CM(np.asfortranarray(g[f"ln_x_{k}"])), dev(jz, g[f"ln_g_{k}"]), dev(jz, g[f"ln_b_{k}"])
+        y, xh, inv = jz.CM.empty("y", dim, N), jz.CM.empty("xh", dim, N), jz.CM.empty("inv", N, 1)
+        jz._lib.check(L.jz_layernorm_forward(y.ptr, xh.ptr, inv.ptr, xm.ptr, gm.ptr, bm.ptr, dim, N, None))
+        assert np.allclose(host(inv), g[f"ln_inv_{k}"], rtol=1e-5)
+        assert np.allclose(xh.to_host(), g[f"ln_xhat_{k}"], rtol=1e-5, atol=1e-5)
+        assert np.allclose(y.to_host(), g[f"ln_y_{k}"], rtol=1e-5, atol=2e-5)
+        dy, xh0, inv0 = jz.CM(np.asfortranarray(g[f"ln_dy_{k}"])), jz.CM(np.asfortranarray(g[f"ln_xhat_{k}"])), dev(jz, g[f"ln_inv_{k}"])
+        dx = jz.CM.empty("dx", dim, N)
+        jz._lib.check(L.jz_layernorm_backward(dx.ptr, dy.ptr, gm.ptr, xh0.ptr, inv0.ptr, dim, N, None))
+        assert np.allclose(dx.to_host(), g[f"ln_dx_{k}"], rtol=1e-5, atol=5e-6)
+
+
 @pytest.mark.parametrize("S,batch", [(1, 1), (9, 4), (32, 3), (70, 3), (128, 64), (1000, 2)])
 def test_softmax_rows_backward(jz, port, S, batch):
     rng = np.random.default_rng(S + batch)
