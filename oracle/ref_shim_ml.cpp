@@ -2,7 +2,8 @@
 //
 // Second shim over the UNMODIFIED reference headers, this one over ml/layer.hpp: the reference's own CPU formulation
 // (generic Matrix<float> operators) of the transformer helpers whose CUDA kernels the jz_* entry points of SURVEY row
-// 8f-3 replace -- row_softmax (ml/layer.hpp:2344-2367) and LayerNorm<float>::forward / backward (:2572-2700).
+// 8f-3 replace -- row_softmax (ml/layer.hpp:2344-2367), LayerNorm<float>::forward / backward (:2572-2700) and the softmax
+// backward expression of TransformerLayer::backward (:3351-3352).
 // Used to pin oracle/jz_oracle.c's restatements of the CUDA kernels (jzo_softmax_rows_batched, jzo_layernorm_*) against
 // what the reference itself computes on the CPU, and to generate tests/golden/ref_ml_golden.npz.
 // Built by `make -C oracle ref-ml` into oracle/_ref/libjzref_ml.so (git-ignored).
@@ -53,6 +54,19 @@ int refml_layernorm_backward(const float* dy, const float* gamma, const float* x
     ln.cached_xhat = owned(xhat, dim, N);
     ln.cached_inv = owned(inv_std, 1, N);
     emit(ln.backward(owned(dy, dim, N), /*update=*/false), dx);
+    return 0;
+}
+
+// dS = A .* (dA - rowsum(A .* dA) * ones(1, seq)) * scale: the reference's CPU spelling of the softmax backward of one
+// attention block, written with its own operators exactly as in TransformerLayer::backward (ml/layer.hpp:3351-3352)
+int refml_softmax_backward(const float* A, const float* dA, size_t seq, float scale, float* dS) {
+    const MF Ai = owned(A, seq, seq), dAi = owned(dA, seq, seq);
+    MF ones_1seq("ones", 1, seq);
+    ones_1seq.ones();
+    auto AodA = hadmd(Ai, dAi);
+    auto row_sum = sum(AodA, 1);
+    auto dSi = hadmd(Ai, dAi - row_sum * ones_1seq) * scale;
+    emit(dSi, dS);
     return 0;
 }
 

@@ -23,6 +23,16 @@ for S in (7, 64, 130):
     y = np.empty_like(x, order="F")
     assert L.refml_row_softmax(p(x), ctypes.c_size_t(S), ctypes.c_size_t(S), p(y)) == 0
     out[f"sm_x_{S}"], out[f"sm_y_{S}"] = x, y
+for S in (9, 70):
+    A = out.get(f"sm_y_{S}")
+    if A is None:
+        x = np.asfortranarray((rng.standard_normal((S, S)) * 2).astype(np.float32))
+        A = np.empty_like(x, order="F")
+        assert L.refml_row_softmax(p(x), ctypes.c_size_t(S), ctypes.c_size_t(S), p(A)) == 0
+    dA = np.asfortranarray(rng.standard_normal((S, S)).astype(np.float32))
+    dS = np.empty_like(dA, order="F")
+    assert L.refml_softmax_backward(p(A), p(dA), ctypes.c_size_t(S), ctypes.c_float(0.125), p(dS)) == 0
+    out[f"smb_A_{S}"], out[f"smb_dA_{S}"], out[f"smb_dS_{S}"] = A, dA, dS
 for dim, N in ((5, 7), (64, 33), (300, 12)):
     x = np.asfortranarray((rng.standard_normal((dim, N)) * 2 + 1).astype(np.float32))
     g = rng.standard_normal(dim).astype(np.float32)

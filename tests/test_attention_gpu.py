@@ -57,6 +57,11 @@ def test_against_the_reference_cpu_formulation(jz):
         jz._lib.check(L.jz_softmax_rows_batched(y.ptr, x.ptr, S, 1, 0, 0.0, None))
         want = g[f"sm_y_{S}"]
         assert np.all(np.abs(y.to_host() - want) <= 1e-5 * np.abs(want) + 1e-12)
+    for S in (9, 70):
+        A, dA, want = g[f"smb_A_{S}"], g[f"smb_dA_{S}"], g[f"smb_dS_{S}"]
+        dA_, dT_, out = jz.CM(np.asfortranarray(A)), jz.CM(np.asfortranarray(dA.T)), jz.CM.empty("dS", S, S)
+        jz._lib.check(L.jz_softmax_rows_backward(out.ptr, dA_.ptr, dT_.ptr, S, 1, 0.125, None))
+        assert np.abs(out.to_host() - want).max() <= 1e-5 * np.abs(want).max()
     for k in ("5x7", "64x33", "300x12"):
         dim, N = (int(v) for v in k.split("x"))
         xm, gm, bm = jz.CM(np.asfortranarray(g[f"ln_x_{k}"])), dev(jz, g[f"ln_g_{k}"]), dev(jz, g[f"ln_b_{k}"])

@@ -3,8 +3,8 @@ The reference's own tests pin those kernels only against PyTorch dumps that cann
 pinned two other ways: (1) against golden vectors generated from the UNMODIFIED reference's CPU formulation of the same
 operations (row_softmax, LayerNorm<float>::forward/backward in ml/layer.hpp, through oracle/ref_shim_ml.cpp;
 tests/golden/ref_ml_golden.npz, scripts/make_golden_ml.py) -- equal to a few ulp, the two being different but equivalent
-operator orders; (2) against float64 formulas.  The softmax backward has no standalone CPU counterpart in the reference
-and is pinned by (2) only."""
+operator orders (the softmax backward against the expression of TransformerLayer::backward, ml/layer.hpp:3351-3352, evaluated
+with the reference's operators); (2) against float64 formulas."""
 import os
 import numpy as np
 import pytest
@@ -38,6 +38,16 @@ def test_layernorm_vs_reference_cpu_formulation(port, ml_golden, k):
     assert np.allclose(y, g[f"ln_y_{k}"], rtol=1e-5, atol=6e-6)
     dx = port.layernorm_backward(g[f"ln_dy_{k}"], g[f"ln_g_{k}"], g[f"ln_xhat_{k}"], g[f"ln_inv_{k}"])
     assert np.allclose(dx, g[f"ln_dx_{k}"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("S", [9, 70])
+def test_softmax_backward_vs_reference_cpu_expression(port, ml_golden, S):
+    """dS = A .* (dA - rowsum(A .* dA)) * scale as TransformerLayer::backward spells it on the CPU (ml/layer.hpp:3351-3352);
+    the CUDA kernel the oracle restates takes dA transposed per block"""
+    A, dA, want = ml_golden[f"smb_A_{S}"], ml_golden[f"smb_dA_{S}"], ml_golden[f"smb_dS_{S}"]
+    dAT = np.asfortranarray(dA.T)
+    got = port.softmax_rows_backward(A.ravel(order="F"), dAT.ravel(order="F"), S, 1, 0.125).reshape(S, S, order="F")
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
 
 
 def test_reference_ml_shim_reproduces_the_golden_vectors(ml_golden):
