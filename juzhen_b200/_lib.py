@@ -16,7 +16,7 @@ JZ_OK, JZ_ERR_SHAPE, JZ_ERR_CUDA, JZ_ERR_OOM, JZ_ERR_ARG, JZ_ERR_UNSUPPORTED = r
 
 UNARY = {"exp": 0, "log": 1, "tanh": 2, "dtanh": 3, "square": 4, "sqrt": 5, "relu": 6, "drelu": 7}
 STEP_AFFINE, STEP_ELEMINV = 100, 101
-GEMM_MODES = {"3xtf32": 0, "tf32": 1, "fp32": 2, "bf16": 3}
+GEMM_MODES = {"3xtf32": 0, "tf32": 1, "fp32": 2}
 
 
 class jz_step(Structure):
@@ -81,6 +81,9 @@ _SIGS = {
                               _F, c_size_t, POINTER(jz_step), c_int, c_int, _S]),
     "jz_gemm_chain_bcast": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, _F, c_size_t,
                                     _F, c_size_t, POINTER(c_void_p), c_int, POINTER(jz_step), c_int, c_int, _S]),
+    "jz_gemm_chain_mcast": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, _F, c_size_t,
+                                    _F, c_size_t, _F, POINTER(jz_step), c_int, c_int, _S]),
+    "jz_gemm_last_splits": (c_int, []),
     "jz_gemm_strided_batched": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, c_size_t, _F, c_size_t,
                                         c_size_t, c_float, _F, c_size_t, c_size_t, c_size_t, c_int, _S]),
     "jz_softmax_rows_batched": (c_int, [_F, _F, c_size_t, c_size_t, c_int, c_float, _S]),

@@ -4,7 +4,7 @@
 // The reference's main() creates the memory pools and the global cuBLAS handle, reads NVIDIA_TF32,
 // runs compute(), then tears everything down.  Here the device side is one call: jz_init() selects
 // the device, sizes the launch geometry and reads the GEMM mode (NVIDIA_TF32=1 keeps its meaning:
-// single-pass TF32 instead of the default fp32-accurate 3xTF32; JZ_GEMM_MODE=3xtf32|tf32|fp32|bf16).
+// single-pass TF32 instead of the default fp32-accurate 3xTF32; JZ_GEMM_MODE=3xtf32|tf32|fp32).
 // No cuBLAS handle is created unless the program was built with -DJZ_LEGACY_CUBLAS_HANDLE for code
 // that calls cuBLAS itself (TransformerLayer, ml/layer.hpp:2896-2926); this backend never uses it.
 #include <chrono>
@@ -25,7 +25,7 @@ static void describe_devices() {
     cudaGetDevice(&dev);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, dev);
-    const char* modes[] = {"3xTF32 (fp32 accuracy)", "TF32", "fp32 SIMT", "bf16"};
+    const char* modes[] = {"3xTF32 (fp32 accuracy)", "TF32", "fp32 SIMT"};
     std::cout << "GPU " << dev << ": " << prop.name << ", sm_" << major << minor << ", " << sms << " SMs, "
               << (mem >> 30) << " GiB" << std::endl;
     std::cout << "GEMM mode: " << modes[jz_get_gemm_mode() & 3] << std::endl;

@@ -19,6 +19,7 @@ struct Ctx {
     std::atomic<uint64_t> launches{0};
     int gemm_mode = JZ_GEMM_3XTF32;
     int gemm_last_path = 0;
+    int gemm_last_splits = 1;   // k-splits per tail tile of the last tensor-core launch (1 = none)
 };
 
 Ctx& ctx();

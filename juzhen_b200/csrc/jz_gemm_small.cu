@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
                                                                    const float* __restrict__ A, size_t lda,
                                                                    const float* __restrict__ B, size_t ldb, float beta,
                                                                    float* C, size_t ldc, ChainParams chain_p,
-                                                                   size_t strideA, size_t strideB, size_t strideC) {
+                                                                   size_t strideA, size_t strideB, size_t strideC, unsigned gx) {
     __shared__ ChainParams chain;
     __shared__ float red[KSPLIT ? SK_WARPS : 1][KSPLIT ? NT : 1][32];
     __shared__ __align__(16) float bline[SK_WARPS][2][32];   // per warp, two iterations deep
@@ -86,9 +86,11 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
     B += size_t(blockIdx.z) * strideB;
     C += size_t(blockIdx.z) * strideC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t i = size_t(blockIdx.x) * 32 + lane;
+    // linear block index = row block + gx * column block (grid.y would cap n at 65535 column blocks)
+    const unsigned bx = blockIdx.x % gx, by = blockIdx.x / gx;
+    const size_t i = size_t(bx) * 32 + lane;
     const size_t il = i < m ? i : m - 1;   // clamped row for loads
-    const size_t j0 = (size_t(blockIdx.y) * (KSPLIT ? 1 : SK_WARPS) + (KSPLIT ? 0 : warp)) * NT;
+    const size_t j0 = (size_t(by) * (KSPLIT ? 1 : SK_WARPS) + (KSPLIT ? 0 : warp)) * NT;
     size_t kbeg = 0, kend = k;
     if (KSPLIT) {
         const size_t per = ((k + 4 * SK_WARPS - 1) / (4 * SK_WARPS)) * 4;   // multiple of 4: slices keep 16-byte phase
@@ -163,10 +165,11 @@ static int launch_small_v(bool vec, size_t m, size_t n, size_t k, float alpha, c
                           cudaStream_t s) {
     const size_t gx = ceil_div(m, size_t(32));
     const size_t gy = ceil_div(n, size_t(NT) * (KSPLIT ? 1 : W));
-    if (gy > 65535 || bt.count > 65535) return fail(JZ_ERR_UNSUPPORTED, "small gemm: n or batch too large");
-    const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)bt.count);
-    if (vec) JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, true, W>), grid, 32 * W, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt.sA, bt.sB, bt.sC);
-    else JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, false, W>), grid, 32 * W, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt.sA, bt.sB, bt.sC);
+    if (gx * gy >= (size_t(1) << 31) || bt.count > 65535) return fail(JZ_ERR_UNSUPPORTED, "small gemm: output or batch too large");
+    const dim3 grid((unsigned)(gx * gy), 1, (unsigned)bt.count);
+    const unsigned gxu = unsigned(gx);
+    if (vec) JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, true, W>), grid, 32 * W, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt.sA, bt.sB, bt.sC, gxu);
+    else JZ_LAUNCH((gemm_small_kernel<TA, TB, NT, KSPLIT, false, W>), grid, 32 * W, 0, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, bt.sA, bt.sB, bt.sC, gxu);
     return JZ_OK;
 }
 // variants: k split over 8 / 16 / 32 warps, 8-column blocks

@@ -1,0 +1,702 @@
+// jz_gemm_tc.cuh -- the tensor-core GEMM kernel behind Matrix<CUDAfloat>::dot / operator* (SURVEY 8a row a17,
+// replacing cublasSgemm, cpp/cumatrix.cu:177-197, and cublasSgemmStridedBatched, ml/layer.hpp:2896-2926).
+// Included by jz_gemm.cu (dispatch) and by the jz_gemm_tc_*.cu translation units that instantiate it (one per
+// arithmetic mode and CTA-group size, so the instantiations compile in parallel).
+//
+// sm_100a: TMA -> shared memory (128B swizzle) -> tcgen05.mma.kind::tf32 with the fp32 accumulator in TMEM ->
+// tcgen05.ld -> coalesced column-major stores.
+//   * warp-specialised CTA: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
+//     (one TMEM lane quarter x one column half each) which, in 3xTF32 mode, also compute the lo operand tiles;
+//   * CG = 2: a CTA pair (cluster 2x1x1, cta_group::2) computes one 256 x TN tile; each CTA loads its 128 rows of
+//     A and its half of the B rows, the leader issues M=256 MMAs that read both CTAs' shared memory.  CG = 1 is the
+//     single-SM 128 x TN variant used for narrow / short / batched products (TN = 64, 128, 256);
+//   * operands are read by TMA straight from the caller's column-major storage, in either major (K-major: box of
+//     32 k x rows, 128B swizzle; MN-major: boxes of 32 rows x 32 k, 128B swizzle with 32-byte atoms); the tensor
+//     maps are 3-D, the third coordinate is the member of a strided batch (blockIdx.z);
+//   * 3xTF32 (MODE_XFORM, fp32 accuracy): every k-block issues A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same
+//     TMEM accumulator.  kind::tf32 reads fp32 words and drops the low 13 mantissa bits, so the raw tile already IS
+//     the hi operand; the epilogue warps compute lo = rna_tf32(x - trunc_tf32(x)) into a second shared buffer;
+//   * two-level accumulation: only kb_per_chunk k-blocks are chained inside TMEM (the tensor core accumulates with
+//     truncation), the epilogue warps add each chunk into fp32 registers with round-to-nearest while the MMA warp
+//     fills the other TMEM half;
+//   * SPLIT-K UNITS: the launch is a list of units in block order -- first `full_tiles` whole tiles (whole waves of
+//     the tile grid, hardware-dispatched in lockstep so the tiles of a wave share their A/B panels in L2), then the
+//     tiles of the partial last wave, each split along k into `splits` units so the tail fills every SM.  The units
+//     of a split tile write their register accumulators to workspace, take a ticket, wait until all `splits` partials
+//     of the tile are there, and each finishes a 1/splits column slice of the tile: partials summed in split order
+//     (bitwise deterministic whatever the arrival order), alpha/beta/chain, store.  All units of a split tile sit in
+//     consecutive blocks of one launch, so the wait cannot deadlock under in-order block dispatch;
+//   * programmatic dependent launch: everything before the first global-memory access (barrier init, TMEM
+//     allocation, tensor-map prefetch) may overlap the tail of the previous kernel in the stream;
+//   * fused all-gather epilogue (multi-GPU): finished elements are also stored to peer images of C, either one
+//     P2P store per peer or ONE multimem.st to an NVSwitch multicast address that lands in every GPU's image.
+#pragma once
+#include <cuda.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "jz_common.cuh"
+#include "jz_math.cuh"
+
+namespace jz {
+namespace tc {
+
+constexpr int BK = 32;               // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;            // tf32: 32 bytes per MMA k-step
+constexpr int TILE_M = 128;          // rows of A per CTA (TMEM lanes)
+constexpr int A_BYTES = TILE_M * BK * 4;  // 16 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int FIRST_EPI_WARP = 2;
+constexpr int NUM_THREADS = 32 * (FIRST_EPI_WARP + NUM_EPI_WARPS);  // TMA warp + MMA warp + 8 epilogue/transform warps
+constexpr int MODE_TF32 = 0;      // single pass over the raw fp32 tiles
+constexpr int MODE_XFORM = 2;     // 3xTF32, lo computed in shared memory by the transform warps
+constexpr int MN_BOX_BYTES = 32 * BK * 4;  // one MN-major TMA box: 32 contiguous rows x 32 k = 4 KB
+constexpr int MAX_SPLITS = 16;
+
+template <int CG, int TN> __host__ __device__ constexpr int b_rows() { return TN / CG; }
+template <int CG, int TN> __host__ __device__ constexpr int b_bytes() { return b_rows<CG, TN>() * BK * 4; }
+template <int CG, int MODE, int TN> __host__ __device__ constexpr int stage_bytes() { return (MODE != MODE_TF32 ? 2 : 1) * (A_BYTES + b_bytes<CG, TN>()); }
+template <int CG, int MODE, int TN> __host__ __device__ constexpr int num_stages() {
+    constexpr int s = (227 * 1024 - 2048) / stage_bytes<CG, MODE, TN>();
+    return s > 8 ? 8 : s;
+}
+template <int CG, int MODE, int TN> __host__ __device__ constexpr int smem_bytes() {
+    return num_stages<CG, MODE, TN>() * stage_bytes<CG, MODE, TN>() + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+struct GemmArgs {
+    size_t m, n, k;
+    float alpha, beta;
+    float* C;
+    size_t ldc;
+    size_t strideC;             // elements between batch members of C
+    unsigned tiles_m, tiles_n;  // in units of (CG*128) x TN tiles
+    unsigned full_tiles;        // units [0, full_tiles) are whole tiles; later units are k-splits of the remaining tiles
+    int splits;                 // k-splits per split tile (>= 2 when full_tiles < tiles_m*tiles_n)
+    int kb_per_split;           // k-blocks per split unit
+    int kb_per_chunk;           // k-blocks accumulated inside TMEM before promotion to registers
+    float* ws;                  // split-K partial tiles: [split tile][split][rank][TN columns][128 rows]
+    unsigned* tickets;          // one per split tile, zeroed before the launch
+    int n_peers;                // additional destinations (peer-GPU images of C, same ldc)
+    float* peers[JZ_MAX_PEERS];
+    float* mc;                  // multicast (NVSwitch) image of C: when set, every element is stored by ONE multimem.st
+    ChainParams chain;
+};
+
+struct Operand {
+    const float* ptr = nullptr;  // raw fp32
+    size_t stride = 0;           // elements between consecutive rows (K-major) / consecutive k (MN-major)
+    size_t batch_stride = 0;     // elements between batch members
+    bool mn = false;             // MN-major: element (r, kk) at kk*stride + r
+    void* owned = nullptr;       // workspace to release
+};
+
+// jz_gemm_tc_*.cu: one definition per MODE x CG
+template <int MODE, int CG>
+int launch_tc_cg(int tn, const Operand& a, const Operand& b, const GemmArgs& args, unsigned batch, cudaStream_t s);
+
+#ifdef JZ_GEMM_TC_IMPL   // ------------------------------------------------------------------ kernel side
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// programmatic dependent launch: wait for the prerequisite grids (and their memory) / let the dependent grid start
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// TO_LEADER: the copy (issued by either CTA of a pair) signals the LEADER CTA's barrier (peer bit cleared);
+// otherwise it signals the issuing CTA's own barrier.  c2 = batch member.
+template <bool TO_LEADER>
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    if constexpr (TO_LEADER) {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+            : "memory");
+    }
+}
+// One operand tile of `ROWS` rows x BK k starting at (row0, kc).
+//   K-major source: one box {BK, ROWS}: ROWS rows of 128 B, 128B swizzle.
+//   MN-major source: ROWS/32 boxes {32 rows, BK}: BK rows of 128 B each holding 32 consecutive operand rows
+//   (4 KB per box, 128B swizzle with 32-byte atoms).
+template <bool MN, int ROWS, bool TO_LEADER>
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* map, uint32_t bar, int kc, int row0, int bz) {
+    if constexpr (MN) {
+#pragma unroll
+        for (int i = 0; i < ROWS / 32; i++) tma_load_3d<TO_LEADER>(dst + i * MN_BOX_BYTES, map, bar, row0 + 32 * i, kc, bz);
+    } else {
+        tma_load_3d<TO_LEADER>(dst, map, bar, kc, row0, bz);
+    }
+}
+template <int CG>
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    if constexpr (CG == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+            "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+            "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// tcgen05.commit: arrive on `bar` (in every CTA of the pair for CG == 2) when all prior MMAs retire
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if constexpr (CG == 2) {
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+            "h"((uint16_t)3)
+            : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    if constexpr (CG == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory operand descriptors (sm_100 format: version 1 at bit 46).
+//   K-major tile: rows of 128 B, 128B swizzle (layout type 2), 8-row groups 1024 B apart (SBO); one UMMA_K step
+//   (8 tf32 = 32 B) advances the start address by 32 B inside the swizzled row.
+//   MN-major tile: the tf32-only canonical layout "128B swizzle, 32B atoms" (layout type 1): an atom is 32
+//   consecutive operand rows (128 B) x 4 k; atoms of the next 4 k follow 512 B later (SBO), the next 32 rows
+//   start one TMA box = 4096 B later (LBO); one UMMA_K step covers two k-atoms = 1024 B.
+template <bool MN>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units
+    if constexpr (MN) {
+        d |= uint64_t(MN_BOX_BYTES >> 4) << 16;   // leading byte offset: between 32-row atoms
+        d |= uint64_t(512 >> 4) << 32;            // stride byte offset: between 4-k atoms
+        d |= uint64_t(1) << 46;
+        d |= uint64_t(1) << 61;                   // SWIZZLE_128B_BASE32B
+    } else {
+        d |= uint64_t(0) << 16;                   // leading byte offset: unused for swizzled K-major
+        d |= uint64_t(1024 >> 4) << 32;           // stride byte offset between 8-row groups
+        d |= uint64_t(1) << 46;
+        d |= uint64_t(2) << 61;                   // SWIZZLE_128B
+    }
+    return d;
+}
+template <bool MN> __host__ __device__ constexpr uint32_t kstep_bytes() { return MN ? 1024u : 32u; }
+// instruction descriptor: tf32 x tf32 -> f32; bit 15 / 16 = A / B is MN-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? 1u << 15 : 0u) | (b_mn ? 1u << 16 : 0u) |
+           (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// named barrier over the 8 epilogue warps only (barrier 0 belongs to __syncthreads)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// one store that NVSwitch replicates into every GPU's image of the buffer (multicast address)
+__device__ __forceinline__ void multimem_st(float* mc_addr, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+}
+
+// lo part of the 3xTF32 split against the hardware's own hi: kind::tf32 drops the low 13 mantissa bits of the
+// fp32 word it reads, so hi = x & 0xFFFFE000 and x - hi is exact in fp32; lo is that remainder rounded to tf32
+// (nearest, ties away: add half an ulp to the magnitude, truncate), so the tensor core reads it unchanged.
+// inf/nan keep their semantics through hi alone (lo = 0 avoids inf - inf).
+__device__ __forceinline__ float tf32_lo_of(float x) {
+    const uint32_t b = __float_as_uint(x);
+    const float d = __fsub_rn(x, __uint_as_float(b & 0xFFFFE000u));
+    const uint32_t r = (__float_as_uint(d) + 0x1000u) & 0xFFFFE000u;
+    return d == d ? __uint_as_float(r) : 0.0f;   // x = inf/nan gives d = nan
+}
+
+// One unit (a whole (CG*128) x TN output tile, or one k-split of it) per CTA group.
+//
+// Barriers (per smem stage): MODE_TF32: TMA of both CTAs -> full (leader) -> MMA -> empty (both).
+// MODE_XFORM: TMA -> full (own CTA) -> epilogue warps write lo -> ready (leader) -> MMA -> empty (both).
+template <int CG, int MODE, int TN, bool AMN, bool BMN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+    constexpr bool XFORM = MODE == MODE_XFORM;
+    constexpr bool TO_LEADER = CG == 2 && !XFORM;   // whose `full` barrier the TMA copies signal
+    constexpr int TILE_N = TN;
+    constexpr int HALF_N = TN / 2;       // columns drained by one epilogue warp
+    constexpr int STAGES = num_stages<CG, MODE, TN>();
+    constexpr int STAGE_BYTES = stage_bytes<CG, MODE, TN>();
+    constexpr int B_ROWS = b_rows<CG, TN>();
+    constexpr int B_BYTES = b_bytes<CG, TN>();
+    constexpr int RAW_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t IDESC = make_idesc_tf32(CG * 128, TILE_N, AMN, BMN);
+    constexpr uint32_t KA = kstep_bytes<AMN>(), KB = kstep_bytes<BMN>();
+    constexpr int TILE_ELEMS = TILE_M * TN;   // one CTA's share of a tile (workspace layout: [column][128 rows])
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ ChainParams s_chain;
+    __shared__ float* s_peers[JZ_MAX_PEERS];
+    stage_chain(&s_chain, args.chain, threadIdx.x);  // visible after the setup barrier below
+    if (threadIdx.x == 32) {  // static indices: direct constant-bank reads (a runtime index would spill the array)
+#pragma unroll
+        for (int q = 0; q < JZ_MAX_PEERS; q++) s_peers[q] = args.peers[q];
+    }
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    // barriers: full[STAGES], empty[STAGES], ready[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto ready_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tmem_full_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
+    auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+    uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+
+    // unit -> (tile, k range).  Whole tiles first, then the k-splits of the remaining tiles.
+    const unsigned unit = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;
+    const int bz = int(blockIdx.z);
+    const int num_kb_total = int((args.k + BK - 1) / BK);
+    unsigned tile = unit;
+    int kb0 = 0, num_kb = num_kb_total, split = -1;
+    unsigned split_tile = 0;
+    if (unit >= args.full_tiles) {
+        const unsigned r = unit - args.full_tiles;
+        split_tile = r / unsigned(args.splits);
+        split = int(r % unsigned(args.splits));
+        tile = args.full_tiles + split_tile;
+        kb0 = split * args.kb_per_split;
+        num_kb = num_kb_total - kb0 < args.kb_per_split ? num_kb_total - kb0 : args.kb_per_split;
+    }
+    // tile coordinates (grouped rasterisation for L2 reuse of the A / B panels)
+    constexpr unsigned GROUP = 8;
+    const unsigned per_group = GROUP * args.tiles_n;
+    const unsigned group_id = tile / per_group;
+    const unsigned first_m = group_id * GROUP;
+    const unsigned group_m = args.tiles_m - first_m < GROUP ? args.tiles_m - first_m : GROUP;
+    const unsigned tm = first_m + (tile % per_group) % group_m;
+    const unsigned tn = (tile % per_group) / group_m;
+    const int m0 = int(tm) * (CG * TILE_M) + int(rank) * TILE_M;  // first row of this CTA
+    const int n0 = int(tn) * TILE_N;
+    const int nb0 = n0 + (CG == 2 ? int(rank) * (TILE_N / 2) : 0);         // first B row (= C column) this CTA loads
+    const int kbc = args.kb_per_chunk;
+    const int num_chunks = (num_kb + kbc - 1) / kbc;
+
+    if (warp == 0 && elect_one()) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        if (elect_one()) {
+            for (int s = 0; s < STAGES; s++) {
+                mbar_init(full_bar(s), 1);
+                mbar_init(empty_bar(s), 1);
+                mbar_init(ready_bar(s), NUM_EPI_WARPS * CG);       // every transform (= epilogue) warp of the pair
+            }
+            for (int b = 0; b < 2; b++) {
+                mbar_init(tmem_full_bar(b), 1);
+                mbar_init(tmem_empty_bar(b), NUM_EPI_WARPS * CG);  // every epilogue warp of the pair
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<CG>(tmem_slot, 2 * TILE_N);
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    // everything above touched no global memory: it may run while the previous kernel of the stream drains
+    pdl_wait();
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < num_kb; kb++) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                if (XFORM) mbar_arrive_expect_tx(full_bar(stage), uint32_t(RAW_BYTES));
+                else if (leader) mbar_arrive_expect_tx(full_bar(stage), uint32_t(STAGE_BYTES) * CG);
+                const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                const int kc = (kb0 + kb) * BK;
+                tma_load_tile<AMN, TILE_M, TO_LEADER>(sa, &tmA, full_bar(stage), kc, m0, bz);
+                tma_load_tile<BMN, B_ROWS, TO_LEADER>(sa + A_BYTES, &tmB, full_bar(stage), kc, nb0, bz);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            uint32_t stage = 0, phase = 0;
+            int chunk = 0, in_chunk = 0;
+            for (int kb = 0; kb < num_kb; kb++) {
+                const uint32_t buf = uint32_t(chunk) & 1u;
+                if (in_chunk == 0) {  // this TMEM buffer must have been drained by every epilogue warp
+                    mbar_wait(tmem_empty_bar(buf), ((uint32_t(chunk) >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                }
+                mbar_wait(XFORM ? ready_bar(stage) : full_bar(stage), phase);
+                tc_fence_after();
+                const bool chunk_end = (in_chunk == kbc - 1) || (kb == num_kb - 1);
+                if (elect_one()) {
+                    const uint32_t d = tmem_base + buf * TILE_N;
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint32_t a_hi = sa, b_hi = sa + A_BYTES;
+                    const uint32_t a_lo = sa + RAW_BYTES, b_lo = sa + RAW_BYTES + A_BYTES;
+                    uint32_t acc = in_chunk == 0 ? 0u : 1u;
+                    if (XFORM) {
+#pragma unroll
+                        for (int ks = 0; ks < BK / UMMA_K; ks++) {
+                            umma_tf32<CG>(d, make_smem_desc<AMN>(a_lo + ks * KA), make_smem_desc<BMN>(b_hi + ks * KB), IDESC, acc);
+                            acc = 1u;
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < BK / UMMA_K; ks++)
+                            umma_tf32<CG>(d, make_smem_desc<AMN>(a_hi + ks * KA), make_smem_desc<BMN>(b_lo + ks * KB), IDESC, 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ks++) {
+                        umma_tf32<CG>(d, make_smem_desc<AMN>(a_hi + ks * KA), make_smem_desc<BMN>(b_hi + ks * KB), IDESC, acc);
+                        acc = 1u;
+                    }
+                    umma_commit<CG>(empty_bar(stage));                   // frees this smem stage (both CTAs)
+                    if (chunk_end) umma_commit<CG>(tmem_full_bar(buf));  // chunk accumulator complete
+                }
+                __syncwarp();
+                if (chunk_end) { chunk++; in_chunk = 0; } else { in_chunk++; }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps: lo-part transform of landed stages (MODE_XFORM), =====================
+        // ===================== TMEM chunks -> fp32 registers (RN) -> global                     =====================
+        const int e = warp - FIRST_EPI_WARP;
+        const int quarter = warp & 3;   // TMEM lane quarter this warp may access (hardware: warp id % 4)
+        const int half = e >> 2;        // which half of the accumulator columns
+        const int lane = threadIdx.x & 31;
+        float acc[HALF_N];
+#pragma unroll
+        for (int i = 0; i < HALF_N; i++) acc[i] = 0.0f;
+        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * HALF_N);
+        const uint32_t empty0 = tmem_empty_bar(0) & 0xFEFFFFFFu, empty1 = tmem_empty_bar(1) & 0xFEFFFFFFu;
+        const uint32_t ready0 = ready_bar(0) & 0xFEFFFFFFu;  // on the leader CTA
+        // Transform and drain interleave in ONE instruction stream per warp, ordered so that neither can starve
+        // the other: k-block j reuses the smem stage of k-block j - STAGES, so it cannot land before the MMAs of
+        // k-block j - STAGES have retired; chunk c (k-blocks c*kbc .. (c+1)*kbc - 1) is therefore complete by the
+        // time k-block (c+1)*kbc + STAGES - 1 lands, and is drained right before that k-block is transformed --
+        // after every k-block the chunk itself (and the next chunk's first STAGES - 1) has been handed to the MMA.
+        constexpr int XT = 32 * NUM_EPI_WARPS;            // transform threads per CTA
+        constexpr int N4 = RAW_BYTES / 16;                // float4 words per stage (A tile then B tile, contiguous)
+        constexpr int PER = N4 / XT;                      // float4 words per thread per stage
+        constexpr int BATCH = PER <= 8 ? PER : (PER % 4 == 0 ? 4 : 3);   // all of a thread's loads in flight together
+        static_assert(N4 % XT == 0 && PER % BATCH == 0, "stage size must divide evenly among the transform threads");
+        const int te = threadIdx.x - 32 * FIRST_EPI_WARP;
+        uint32_t stage = 0, phase = 0;
+        int next_drain = 0;
+        const int kb_end = XFORM ? num_kb : 0;
+        for (int kb = 0; kb <= kb_end; kb++) {
+            while (next_drain < num_chunks && (kb >= kb_end || (next_drain + 1) * kbc + STAGES - 1 <= kb)) {
+                const int chunk = next_drain++;
+                const uint32_t buf = uint32_t(chunk) & 1u;
+                mbar_wait(tmem_full_bar(buf), (uint32_t(chunk) >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int p = 0; p < HALF_N / 32; p++) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(lane_addr + buf * TILE_N + p * 32, r);
+#pragma unroll
+                    for (int c = 0; c < 32; c++) acc[p * 32 + c] = __fadd_rn(acc[p * 32 + c], __uint_as_float(r[c]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(buf ? empty1 : empty0);  // on the leader CTA's barrier
+            }
+            if (XFORM && kb < kb_end) {
+                mbar_wait(full_bar(stage), phase);
+                const float4* src = reinterpret_cast<const float4*>(gen_base + stage * STAGE_BYTES) + te;
+                float4* dst = reinterpret_cast<float4*>(gen_base + stage * STAGE_BYTES + RAW_BYTES) + te;
+#pragma unroll
+                for (int i0 = 0; i0 < PER; i0 += BATCH) {
+                    float4 v[BATCH];
+#pragma unroll
+                    for (int u = 0; u < BATCH; u++) v[u] = src[(i0 + u) * XT];
+#pragma unroll
+                    for (int u = 0; u < BATCH; u++)
+                        dst[(i0 + u) * XT] = make_float4(tf32_lo_of(v[u].x), tf32_lo_of(v[u].y), tf32_lo_of(v[u].z), tf32_lo_of(v[u].w));
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ready0 + 8u * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        float* const Cb = args.C + size_t(bz) * args.strideC;
+        const size_t ldc = args.ldc;
+        if (split < 0) {
+            // ---- whole tile: alpha/beta/chain on the register accumulators, coalesced column stores
+            const size_t row = size_t(m0) + quarter * 32 + lane;
+            const bool row_ok = row < args.m;
+            const size_t ncol0 = size_t(n0) + half * HALF_N;
+#pragma unroll
+            for (int p = 0; p < HALF_N / 32; p++) {
+                const size_t colp = ncol0 + p * 32;
+                if (colp < args.n) {  // warp-uniform
+                    const int ncols = args.n - colp < 32 ? int(args.n - colp) : 32;
+                    float v[32];
+#pragma unroll
+                    for (int c = 0; c < 32; c++) v[c] = args.alpha * acc[p * 32 + c];
+                    if (args.beta != 0.0f && row_ok) {
+                        const float* src = Cb + row + colp * ldc;  // running pointer: no 32 hoisted addresses
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            if (c < ncols) v[c] += args.beta * *src;
+                            src += ldc;
+                        }
+                    }
+                    if (s_chain.n) apply_chain<32>(v, s_chain);
+                    // a warp writes 32 consecutive floats (128 B) per column.  Multi-GPU (fused all-gather): either ONE
+                    // multimem.st per element to the multicast image (NVSwitch replicates it into every GPU's C,
+                    // this one included), or the local C plus one P2P store per peer image.
+                    if (row_ok) {
+                        if (args.mc) {
+                            float* dst = args.mc + row + colp * ldc;
+#pragma unroll
+                            for (int c = 0; c < 32; c++) {
+                                if (c < ncols) multimem_st(dst, v[c]);
+                                dst += ldc;
+                            }
+                        } else {
+                            for (int d = 0; d <= args.n_peers; d++) {
+                                float* dst = (d == 0 ? Cb : s_peers[d - 1]) + row + colp * ldc;
+#pragma unroll
+                                for (int c = 0; c < 32; c++) {
+                                    if (c < ncols) *dst = v[c];
+                                    dst += ldc;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            // ---- k-split unit: park the raw partial tile, then finish a 1/splits column slice of the tile
+            const int S = args.splits;
+            float* const ws_tile = args.ws + size_t(split_tile) * size_t(S) * (CG * TILE_ELEMS);   // [split][rank][col][row]
+            {
+                float* dst = ws_tile + (size_t(split) * CG + rank) * TILE_ELEMS + size_t(half * HALF_N) * TILE_M + quarter * 32 + lane;
+#pragma unroll
+                for (int c = 0; c < HALF_N; c++) __stcg(dst + c * TILE_M, acc[c]);
+            }
+            __threadfence();
+            epi_bar_sync();
+            if (te == 0) {
+                unsigned* tk = args.tickets + split_tile;
+                atomicAdd(tk, 1u);
+                const unsigned want = unsigned(S) * CG;
+                while (ld_acquire_gpu(tk) < want) __nanosleep(40);
+            }
+            epi_bar_sync();
+            __threadfence();
+            const int c_begin = split * TILE_N / S, c_end = (split + 1) * TILE_N / S;
+            const int r_local = te & (TILE_M - 1);
+            const size_t row = size_t(m0) + r_local;
+            if (row < args.m) {
+                for (int c = c_begin + (te >> 7); c < c_end; c += 2) {
+                    const size_t col = size_t(n0) + c;
+                    if (col >= args.n) break;
+                    const float* src = ws_tile + size_t(rank) * TILE_ELEMS + size_t(c) * TILE_M + r_local;
+                    float sum = __ldcg(src);
+                    for (int s = 1; s < S; s++) sum = __fadd_rn(sum, __ldcg(src + size_t(s) * (CG * TILE_ELEMS)));
+                    float v[1] = {args.alpha * sum};
+                    if (args.beta != 0.0f) v[0] += args.beta * Cb[row + col * ldc];
+                    if (s_chain.n) apply_chain<1>(v, s_chain);
+                    if (args.mc) {
+                        multimem_st(args.mc + row + col * ldc, v[0]);
+                    } else {
+                        Cb[row + col * ldc] = v[0];
+                        for (int d = 0; d < args.n_peers; d++) s_peers[d][row + col * ldc] = v[0];
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc<CG>(tmem_base, 2 * TILE_N);
+}
+
+// ----------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+// Tensor map of one operand over its source storage, zero OOB fill; third dimension = batch member.
+//   K-major ([rows][k], row stride `stride_elems`): dims {k, rows, batch}, box {32, box_rows, 1}, 128B swizzle.
+//   MN-major ([k][rows], k stride `stride_elems`): dims {rows, k, batch}, box {32 rows, 32 k, 1}, 128B swizzle / 32B atoms.
+static int make_map(CUtensorMap* map, const Operand& op, size_t rows, size_t k, int box_rows, unsigned batch) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(JZ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const bool mn = op.mn;
+    cuuint64_t dims[3] = {cuuint64_t(mn ? rows : k), cuuint64_t(mn ? k : rows), cuuint64_t(batch)};
+    // a single product has no batch stride: use the natural one (dim1 * stride0), it is never stepped
+    size_t bstride = batch > 1 ? op.batch_stride : size_t(dims[1]) * op.stride;
+    if (bstride * sizeof(float) >= (size_t(1) << 40)) bstride = 4;
+    cuuint64_t strides[2] = {cuuint64_t(op.stride) * sizeof(float), cuuint64_t(bstride) * sizeof(float)};
+    cuuint32_t box[3] = {cuuint32_t(BK), cuuint32_t(mn ? BK : box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(op.ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(JZ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+    return JZ_OK;
+}
+
+static bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("JZ_GEMM_NO_PDL");
+        return !(e && e[0] && e[0] != '0');
+    }();
+    return on;
+}
+
+// args.tiles_m / tiles_n / full_tiles / splits / kb_per_split / ws / tickets are filled by the caller (plan_units)
+template <int CG, int MODE, int TN, bool AMN, bool BMN>
+static int launch_tc(const Operand& a, const Operand& b, const GemmArgs& args, unsigned batch, cudaStream_t s) {
+    alignas(64) CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_map(&ma, a, args.m, args.k, TILE_M, batch)) != JZ_OK) return rc;
+    if ((rc = make_map(&mb, b, args.n, args.k, b_rows<CG, TN>(), batch)) != JZ_OK) return rc;
+    auto kern = gemm_tcgen05_kernel<CG, MODE, TN, AMN, BMN>;
+    constexpr int SMEM = smem_bytes<CG, MODE, TN>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        JZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_done = true;
+    }
+    const unsigned tiles = args.tiles_m * args.tiles_n;
+    const unsigned units = args.full_tiles + (tiles - args.full_tiles) * unsigned(args.splits);
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(units * CG, 1, batch);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, args);
+    ctx().launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return cuda_fail(e, "gemm_tcgen05_kernel launch");
+    return JZ_OK;
+}
+
+// operand majors are compile-time (they select TMA box shapes and descriptor layouts)
+template <int CG, int MODE, int TN>
+static int launch_tc_major(const Operand& a, const Operand& b, const GemmArgs& args, unsigned batch, cudaStream_t s) {
+    if (a.mn) return b.mn ? launch_tc<CG, MODE, TN, true, true>(a, b, args, batch, s) : launch_tc<CG, MODE, TN, true, false>(a, b, args, batch, s);
+    return b.mn ? launch_tc<CG, MODE, TN, false, true>(a, b, args, batch, s) : launch_tc<CG, MODE, TN, false, false>(a, b, args, batch, s);
+}
+
+#endif  // JZ_GEMM_TC_IMPL
+
+}  // namespace tc
+}  // namespace jz

@@ -79,7 +79,6 @@ static int do_init(int device) {
         if (!std::strcmp(gm, "3xtf32")) g_ctx.gemm_mode = JZ_GEMM_3XTF32;
         else if (!std::strcmp(gm, "tf32")) g_ctx.gemm_mode = JZ_GEMM_TF32;
         else if (!std::strcmp(gm, "fp32")) g_ctx.gemm_mode = JZ_GEMM_FP32_SIMT;
-        else if (!std::strcmp(gm, "bf16")) g_ctx.gemm_mode = JZ_GEMM_BF16;
     }
     g_ctx.inited = true;
     return JZ_OK;
@@ -240,7 +239,7 @@ int jz_sync(jz_stream_t stream) {
 uint64_t jz_launch_count(void) { return g_ctx.launches.load(); }
 
 int jz_set_gemm_mode(int mode) {
-    if (mode < JZ_GEMM_3XTF32 || mode > JZ_GEMM_BF16) return fail(JZ_ERR_ARG, "bad gemm mode %d", mode);
+    if (mode < JZ_GEMM_3XTF32 || mode > JZ_GEMM_FP32_SIMT) return fail(JZ_ERR_ARG, "bad gemm mode %d", mode);
     g_ctx.gemm_mode = mode;
     return JZ_OK;
 }
