@@ -84,12 +84,12 @@ __global__ void __launch_bounds__(256) causal_mask_kernel(float* s, size_t S, si
 // floats: they are read coalesced along b and parked transposed in shared memory ([S][33]), so both operands are
 // consumed with lanes along a.
 __global__ void __launch_bounds__(32 * AT_WARPS) softmax_rows_backward_kernel(float* dS, const float* A, const float* dAT,
-                                                                              int S, float scale) {
+                                                                              int S, float scale, unsigned row_blocks) {
     extern __shared__ float dtile[];   // [S][33]: dtile[b*33 + a_local] = dA(a0 + a_local, b)
     __shared__ float red[AT_WARPS][32];
     const int lane = threadIdx.x, w = threadIdx.y;
-    const int a0 = blockIdx.x * 32;
-    const size_t blk = size_t(blockIdx.y) * size_t(S) * size_t(S);
+    const int a0 = int(blockIdx.x % row_blocks) * 32;   // linear grid: row block + row_blocks * batch member
+    const size_t blk = size_t(blockIdx.x / row_blocks) * size_t(S) * size_t(S);
     // stage: warp w copies columns a_local = w, w + 8, ... of dAT (each S contiguous floats), lanes along b
     for (int al = w; al < 32; al += AT_WARPS) {
         const int a = a0 + al;
@@ -109,6 +109,45 @@ __global__ void __launch_bounds__(32 * AT_WARPS) softmax_rows_backward_kernel(fl
     for (int b = w; b < S; b += AT_WARPS) {
         const float av = A[base + size_t(b) * S];
         dS[base + size_t(b) * S] = av * (dtile[b * 33 + lane] - rs) * scale;
+    }
+}
+
+// Same, for key ranges that do not fit in shared memory at once (seq_len > 1551; the reference kernel has no limit):
+// keys are staged `chunk` at a time, once for the row sums and once more for the output (the second read of dAT comes
+// from L2).  The per-warp partial sums accumulate over the chunks in the same b order as the one-pass kernel.
+__global__ void __launch_bounds__(32 * AT_WARPS) softmax_rows_backward_long_kernel(float* dS, const float* A, const float* dAT,
+                                                                                   int S, float scale, unsigned row_blocks, int chunk) {
+    extern __shared__ float dtile[];   // [chunk][33]
+    __shared__ float red[AT_WARPS][32];
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const int a0 = int(blockIdx.x % row_blocks) * 32;
+    const size_t blk = size_t(blockIdx.x / row_blocks) * size_t(S) * size_t(S);
+    const int a = a0 + lane;
+    const bool ok = a < S;
+    const size_t base = blk + size_t(ok ? a : 0);
+    float rs = 0.0f;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int b0 = 0; b0 < S; b0 += chunk) {
+            const int nb = S - b0 < chunk ? S - b0 : chunk;
+            for (int al = w; al < 32; al += AT_WARPS) {
+                const int aa = a0 + al;
+#pragma unroll 8
+                for (int b = lane; b < nb; b += 32) dtile[b * 33 + al] = aa < S ? dAT[blk + size_t(aa) * S + b0 + b] : 0.0f;
+            }
+            __syncthreads();
+            if (pass == 0) {
+#pragma unroll 8
+                for (int b = w; b < nb; b += AT_WARPS) rs += A[base + size_t(b0 + b) * S] * dtile[b * 33 + lane];
+            } else if (ok) {
+#pragma unroll 8
+                for (int b = w; b < nb; b += AT_WARPS) {
+                    const float av = A[base + size_t(b0 + b) * S];
+                    dS[base + size_t(b0 + b) * S] = av * (dtile[b * 33 + lane] - rs) * scale;
+                }
+            }
+            __syncthreads();
+        }
+        if (pass == 0) rs = fold_warps<AT_WARPS>(rs, red, [](float p, float q) { return p + q; }, 0.0f);
     }
 }
 
@@ -273,15 +312,24 @@ int jz_softmax_rows_backward(float* dS, const float* A, const float* dAT, size_t
     JZ_INIT_OR_RETURN();
     if (seq_len == 0 || batch == 0) return JZ_OK;
     if (!dS || !A || !dAT) return fail(JZ_ERR_ARG, "jz_softmax_rows_backward: null pointer");
-    const size_t smem = seq_len * 33 * sizeof(float);
-    if (smem > kMaxDynSmem || batch > 65535) return fail(JZ_ERR_UNSUPPORTED, "jz_softmax_rows_backward: seq_len > 1551 or batch > 65535");
+    const size_t row_blocks = ceil_div(seq_len, size_t(32));
+    if (row_blocks * batch >= (size_t(1) << 31) || seq_len >= (size_t(1) << 31)) return fail(JZ_ERR_UNSUPPORTED, "jz_softmax_rows_backward: more than 2^31 row blocks");
+    const unsigned grid = unsigned(row_blocks * batch);
+    const dim3 block(32, AT_WARPS, 1);
     static bool attr_done = false;
     if (!attr_done) {
         JZ_CUDA(cudaFuncSetAttribute(softmax_rows_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem)));
+        JZ_CUDA(cudaFuncSetAttribute(softmax_rows_backward_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem)));
         attr_done = true;
     }
-    const dim3 grid((unsigned)ceil_div(seq_len, size_t(32)), (unsigned)batch, 1), block(32, AT_WARPS, 1);
-    JZ_LAUNCH(softmax_rows_backward_kernel, grid, block, smem, as_stream(stream), dS, A, dAT, int(seq_len), scale);
+    const size_t smem = seq_len * 33 * sizeof(float);
+    if (smem <= kMaxDynSmem) {
+        JZ_LAUNCH(softmax_rows_backward_kernel, grid, block, smem, as_stream(stream), dS, A, dAT, int(seq_len), scale, unsigned(row_blocks));
+    } else {   // keys staged 768 at a time (two CTAs per SM stay resident)
+        const int chunk = 768;
+        JZ_LAUNCH(softmax_rows_backward_long_kernel, grid, block, size_t(chunk) * 33 * sizeof(float), as_stream(stream), dS, A, dAT,
+                  int(seq_len), scale, unsigned(row_blocks), chunk);
+    }
     return JZ_OK;
 }
 

@@ -225,17 +225,53 @@ __global__ void __launch_bounds__(kThreads) chain_s(float* out, const float* in,
     }
 }
 
-// fused Adam step (ml/util.cuh:152-163): same arithmetic, vectorised, 12 B read + 12 B write
-__global__ void __launch_bounds__(kThreads) adam_kernel(float* g, float* m, float* v, size_t n, float alpha,
-                                                        float beta1, float beta2, float eps, float bc1, float bc2) {
-    for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += size_t(gridDim.x) * kThreads) {
-        const float gi = g[i];
-        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        g[i] = alpha * (mi * bc1) / (sqrtf(vi * bc2) + eps);
+// ---- Adam step (adam_update_kernel, ml/util.cuh:152-163).  Arithmetic follows the reference's CPU adam_update<float>
+// (ml/util.cuh:223-245, documented there as bit-identical to its generic operator formulation), one rounding per
+// operator and the "+ 0.0f" of every scale(): bit-exact with it given the same bc1 / bc2, which the tests pin against
+// golden vectors from the unmodified reference.  24 B/elem (g, m, v read and written): 128-bit accesses, kUnroll
+// independent 128-bit loads per array in flight per thread, one tile per CTA like the map kernels.
+struct AdamP { float alpha, beta1, beta2, eps, bc1, bc2, omb1, omb2; };
+__device__ __forceinline__ void adam_elem(float& g, float& m, float& v, const AdamP& p) {
+    const float mi = __fadd_rn(__fadd_rn(__fmul_rn(p.beta1, m), 0.0f), __fadd_rn(__fmul_rn(p.omb1, g), 0.0f));
+    const float vi = __fadd_rn(__fadd_rn(__fmul_rn(p.beta2, v), 0.0f), __fadd_rn(__fmul_rn(p.omb2, __fmul_rn(g, g)), 0.0f));
+    m = mi;
+    v = vi;
+    const float mh = __fadd_rn(__fmul_rn(p.bc1, mi), 0.0f);
+    const float vh = __fadd_rn(__fmul_rn(p.bc2, vi), 0.0f);
+    const float den = __fadd_rn(__fsqrt_rn(vh), p.eps);
+    g = __fmul_rn(__fadd_rn(__fmul_rn(p.alpha, mh), 0.0f), __frcp_rn(den));   // (float)(1.0 / den): innocuous double rounding
+}
+__global__ void __launch_bounds__(kThreads) adam_v4(float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n, AdamP p) {
+    const size_t n4 = n >> 2;
+    float4* g4 = reinterpret_cast<float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (size_t base = size_t(blockIdx.x) * (kThreads * kUnroll); base < n4; base += size_t(gridDim.x) * (kThreads * kUnroll)) {
+        float4 a[kUnroll], b[kUnroll], c[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + u * kThreads + threadIdx.x;
+            if (i < n4) { a[u] = g4[i]; b[u] = m4[i]; c[u] = v4[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + u * kThreads + threadIdx.x;
+            if (i < n4) {
+                adam_elem(a[u].x, b[u].x, c[u].x, p);
+                adam_elem(a[u].y, b[u].y, c[u].y, p);
+                adam_elem(a[u].z, b[u].z, c[u].z, p);
+                adam_elem(a[u].w, b[u].w, c[u].w, p);
+                g4[i] = a[u]; m4[i] = b[u]; v4[i] = c[u];
+            }
+        }
     }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {   // tail of fewer than 4 elements
+        const size_t i = (n4 << 2) + threadIdx.x;
+        adam_elem(g[i], m[i], v[i], p);
+    }
+}
+__global__ void __launch_bounds__(kThreads) adam_s(float* g, float* m, float* v, size_t n, AdamP p) {   // unaligned pointers
+    for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += size_t(gridDim.x) * kThreads) adam_elem(g[i], m[i], v[i], p);
 }
 
 static inline unsigned grid_for(size_t tiles) {
@@ -424,8 +460,11 @@ int jz_adam_update(float* g, float* m, float* v, size_t n, float alpha, float be
     JZ_INIT_OR_RETURN();
     if (n == 0) return JZ_OK;
     if (!g || !m || !v) return fail(JZ_ERR_ARG, "jz_adam_update: null pointer");
-    JZ_LAUNCH(adam_kernel, grid_for(ceil_div(n, size_t(kThreads) * kUnroll)), kThreads, 0, as_stream(stream), g, m,
-              v, n, alpha, beta1, beta2, eps, bc1, bc2);
+    AdamP p{alpha, beta1, beta2, eps, bc1, bc2, 1 - beta1, 1 - beta2};
+    if (aligned16(g) && aligned16(m) && aligned16(v))
+        JZ_LAUNCH(adam_v4, grid_for(ceil_div(n >> 2, size_t(kThreads) * kUnroll)), kThreads, 0, as_stream(stream), g, m, v, n, p);
+    else
+        JZ_LAUNCH(adam_s, grid_for(ceil_div(n, size_t(kThreads) * kUnroll)), kThreads, 0, as_stream(stream), g, m, v, n, p);
     return JZ_OK;
 }
 

@@ -184,6 +184,13 @@ class Oracle:
         self._fn("layernorm_backward")(_f(dy), _f(gamma), _f(xhat), _f(inv_std), _f(dx), c_size_t(dim), c_size_t(N))
         return dx
 
+    def adam_update(self, g, m, v, alpha, beta1, beta2, eps, bc1, bc2):
+        """one Adam step (ml/util.cuh:223-245); returns the updated (g, m, v) copies"""
+        g, m, v = (np.array(x, dtype=np.float32, copy=True).ravel() for x in (g, m, v))
+        self._fn("adam_update")(_f(g), _f(m), _f(v), c_size_t(g.size), c_float(alpha), c_float(beta1), c_float(beta2),
+                                c_float(eps), c_float(bc1), c_float(bc2))
+        return g, m, v
+
     def norm(self, x):
         x = np.ascontiguousarray(x, dtype=np.float32)
         return float(self._fn("norm", c_float)(_f(x), c_size_t(x.size)))

@@ -70,4 +70,20 @@ int refml_softmax_backward(const float* A, const float* dA, size_t seq, float sc
     return 0;
 }
 
+// One Adam step through the reference's own adam_update<float> (ml/util.cuh:165-257; the fused CPU branch :223-245,
+// which the reference documents as bit-identical to its generic operator formulation).  g, m, v are updated in place;
+// `iteration` is the step counter t (bias corrections 1/(1 - beta^t) are computed inside, in double).
+int refml_adam_update(float* g, float* m, float* v, size_t n, float alpha, float beta1, float beta2, float eps, int iteration) {
+    adam_state<float> st((double)alpha, n, 1);
+    st.iteration = iteration;
+    st.alpha = alpha; st.beta1 = beta1; st.beta2 = beta2; st.eps = eps;
+    st.m = owned(m, n, 1);
+    st.v = owned(v, n, 1);
+    MF upd = adam_update(owned(g, n, 1), st);
+    std::memcpy(g, upd.data(), n * sizeof(float));
+    std::memcpy(m, st.m.data(), n * sizeof(float));
+    std::memcpy(v, st.v.data(), n * sizeof(float));
+    return 0;
+}
+
 }  // extern "C"

@@ -46,5 +46,19 @@ for dim, N in ((5, 7), (64, 33), (300, 12)):
     k = f"{dim}x{N}"
     out.update({f"ln_x_{k}": x, f"ln_g_{k}": g, f"ln_b_{k}": b, f"ln_y_{k}": y, f"ln_xhat_{k}": xh, f"ln_inv_{k}": inv,
                 f"ln_dy_{k}": dy, f"ln_dx_{k}": dx})
+# Adam: three consecutive steps of the reference's adam_update<float> (ml/util.cuh:165-257) from its own initial state
+n = 4099
+g0 = (rng.standard_normal((3, n)) * np.array([[1.0], [1e-3], [30.0]])).astype(np.float32)
+m = np.zeros(n, dtype=np.float32)
+v = np.zeros(n, dtype=np.float32)
+out["adam_g_in"] = g0.copy()
+upd = np.empty_like(g0)
+for t in range(3):
+    g = g0[t].copy()
+    assert L.refml_adam_update(p(g), p(m), p(v), ctypes.c_size_t(n), ctypes.c_float(0.01), ctypes.c_float(0.9),
+                               ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_int(t + 1)) == 0
+    upd[t] = g
+    out[f"adam_m_{t + 1}"], out[f"adam_v_{t + 1}"] = m.copy(), v.copy()
+out["adam_update"] = upd
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_ml_golden.npz"), **out)
 print("wrote", len(out), "arrays")

@@ -76,7 +76,7 @@ def test_against_the_reference_cpu_formulation(jz):
         assert np.allclose(dx.to_host(), g[f"ln_dx_{k}"], rtol=1e-5, atol=5e-6)
 
 
-@pytest.mark.parametrize("S,batch", [(1, 1), (9, 4), (32, 3), (70, 3), (128, 64), (1000, 2)])
+@pytest.mark.parametrize("S,batch", [(1, 1), (9, 4), (32, 3), (70, 3), (128, 64), (1000, 2), (1551, 1), (1552, 1), (2100, 2)])
 def test_softmax_rows_backward(jz, port, S, batch):
     rng = np.random.default_rng(S + batch)
     A = port.softmax_rows_batched(rng.standard_normal(S * S * batch).astype(np.float32), S, batch)

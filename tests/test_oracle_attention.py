@@ -64,6 +64,30 @@ def test_reference_ml_shim_reproduces_the_golden_vectors(ml_golden):
     assert np.array_equal(y.view(np.uint32), ml_golden["sm_y_64"].view(np.uint32))
 
 
+def test_adam_restatement_bit_exact_vs_reference_cpu(port, ml_golden):
+    """oracle/jz_oracle.c:jzo_adam_update against three consecutive steps of the unmodified reference's
+    adam_update<float> (ml/util.cuh:165-257); where libjzref_ml.so travelled, that library against the fixture too"""
+    g_in = ml_golden["adam_g_in"]
+    n = g_in.shape[1]
+    m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for t in range(3):
+        bc1 = np.float32(1.0 / (1.0 - np.float64(np.float32(0.9)) ** (t + 1)))
+        bc2 = np.float32(1.0 / (1.0 - np.float64(np.float32(0.999)) ** (t + 1)))
+        g, m, v = port.adam_update(g_in[t], m, v, 0.01, 0.9, 0.999, 1e-8, bc1, bc2)
+        assert np.array_equal(g.view(np.uint32), ml_golden["adam_update"][t].view(np.uint32))
+        assert np.array_equal(m.view(np.uint32), ml_golden[f"adam_m_{t + 1}"].view(np.uint32))
+        assert np.array_equal(v.view(np.uint32), ml_golden[f"adam_v_{t + 1}"].view(np.uint32))
+    import ctypes
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libjzref_ml.so")
+    if os.path.exists(so):
+        L = ctypes.CDLL(so)
+        g, m, v = g_in[0].copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        assert L.refml_adam_update(P(g), P(m), P(v), ctypes.c_size_t(n), ctypes.c_float(0.01), ctypes.c_float(0.9),
+                                   ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_int(1)) == 0
+        assert np.array_equal(g.view(np.uint32), ml_golden["adam_update"][0].view(np.uint32))
+
+
 def blocks(x, S, batch):
     """(S, S*batch) column-major flat buffer -> [batch][a][b]"""
     return x.reshape(batch, S, S).transpose(0, 2, 1)   # flat index = blk*S*S + b*S + a

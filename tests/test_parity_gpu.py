@@ -8,6 +8,8 @@ reductions <= 1e-5 relative; GEMM is in tests/test_gemm_gpu.py.  The arithmetic 
 (affine, axpby, hadamard, A/B, eleminv, square, relu) are in fact held to BIT-EXACT because the
 kernels use the same unfused fp32 operations as the x86-64 reference.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -353,20 +355,38 @@ def test_rng_moments_and_determinism(jz):
     assert u.min() >= 0 and u.max() < 1 and abs(u.mean() - 0.5) < 2e-3
 
 
-def test_adam_step_matches_reference_kernel_formula(jz):
+def adam_bc(beta, t):
+    """bias correction as the reference's CPU path computes it: double pow, double reciprocal, float cast (ml/util.cuh:226-227)"""
+    return np.float32(1.0 / (1.0 - np.float64(np.float32(beta)) ** t))
+
+
+def test_adam_steps_bit_exact_vs_reference_cpu_adam_update(jz, port):
+    """three consecutive jz_adam_update steps against golden vectors produced by the UNMODIFIED reference's
+    adam_update<float> (ml/util.cuh:165-257, through oracle/ref_shim_ml.cpp; scripts/make_golden_ml.py): g, m and v
+    bit for bit, and the same against the C oracle's restatement on a larger, unaligned, odd-length case"""
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ml_golden.npz"))
+    g_in = G["adam_g_in"]
+    n = g_in.shape[1]
+    L = jz.lib()
+    md, vd = flat(jz, np.zeros(n, np.float32)), flat(jz, np.zeros(n, np.float32))
+    for t in range(3):
+        gd = flat(jz, g_in[t])
+        jz._lib.check(L.jz_adam_update(gd.ptr, md.ptr, vd.ptr, n, 0.01, 0.9, 0.999, 1e-8, adam_bc(0.9, t + 1), adam_bc(0.999, t + 1), None))
+        assert same_bits(gd.to_host().ravel(), G["adam_update"][t]), f"update, step {t + 1}"
+        assert same_bits(md.to_host().ravel(), G[f"adam_m_{t + 1}"]) and same_bits(vd.to_host().ravel(), G[f"adam_v_{t + 1}"])
     rng = np.random.default_rng(11)
-    n = 10007
-    g = rng.standard_normal(n).astype(np.float32); m = rng.standard_normal(n).astype(np.float32) * 0.1
-    v = np.abs(rng.standard_normal(n)).astype(np.float32) * 0.01
-    gd, md, vd = flat(jz, g), flat(jz, m), flat(jz, v)
-    al, b1, b2, eps, t = 0.01, 0.9, 0.999, 1e-8, 3
-    bc1, bc2 = 1 / (1 - b1 ** t), 1 / (1 - b2 ** t)
-    jz._lib.check(jz.lib().jz_adam_update(gd.ptr, md.ptr, vd.ptr, n, al, b1, b2, eps, bc1, bc2, None))
-    m2 = b1 * m.astype(np.float64) + (1 - b1) * g
-    v2 = b2 * v.astype(np.float64) + (1 - b2) * g.astype(np.float64) ** 2
-    upd = al * (m2 * bc1) / (np.sqrt(v2 * bc2) + eps)
-    assert np.allclose(md.to_host().ravel(), m2, rtol=1e-5, atol=1e-6) and np.allclose(vd.to_host().ravel(), v2, rtol=1e-5, atol=1e-7)
-    assert np.allclose(gd.to_host().ravel(), upd, rtol=1e-4, atol=1e-7)
+    n = 1_000_003
+    g = rng.standard_normal(n + 1).astype(np.float32); m = (rng.standard_normal(n + 1) * 0.1).astype(np.float32)
+    v = (np.abs(rng.standard_normal(n + 1)) * 0.01).astype(np.float32)
+    for off in (0, 1):          # off = 1: pointers 4 bytes past a 16-byte boundary -> scalar kernel
+        gd, md, vd = flat(jz, g), flat(jz, m), flat(jz, v)
+        bc1, bc2 = adam_bc(0.9, 7), adam_bc(0.999, 7)
+        jz._lib.check(L.jz_adam_update(gd.ptr + 4 * off, md.ptr + 4 * off, vd.ptr + 4 * off, n, 0.003, 0.9, 0.999, 1e-8, bc1, bc2, None))
+        wg, wm, wv = port.adam_update(g[off:off + n], m[off:off + n], v[off:off + n], 0.003, 0.9, 0.999, 1e-8, bc1, bc2)
+        assert same_bits(gd.to_host().ravel()[off:off + n], wg) and same_bits(md.to_host().ravel()[off:off + n], wm)
+        assert same_bits(vd.to_host().ravel()[off:off + n], wv)
+        if off:   # the element in front of the window did not move
+            assert gd.to_host().ravel()[0] == g[0] and md.to_host().ravel()[0] == m[0]
 
 
 # ------------------------------------------------------------------ exhaustive accuracy sweeps (every fp32 input)
