@@ -31,6 +31,12 @@ inline cudaStream_t as_stream(jz_stream_t s) { return reinterpret_cast<cudaStrea
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
 
+// Zero-initialised ticket counters (kTicketSlots unsigned), one block per (device, stream).  Kernels on a stream are
+// serialised and every kernel that uses the block leaves its counters at zero again, so the block is never shared by
+// two running kernels and never needs a memset after the first use.  nullptr on allocation failure.
+constexpr size_t kTicketSlots = 4096;
+unsigned* tickets_for(cudaStream_t s);
+
 // temporary workspace from the stream-ordered pool (bytes), released with ws_free
 int ws_alloc(void** p, size_t bytes, cudaStream_t s);
 int ws_free(void* p, cudaStream_t s);

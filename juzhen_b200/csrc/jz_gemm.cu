@@ -260,7 +260,7 @@ static int chunk_kb(bool split) {
 // less than one wave) are split along k so that the tail occupies every SM (pair).  A split must keep at least
 // MIN_KB k-blocks so the fix-up (one partial tile out and back through L2) stays a fraction of its mainloop.
 // JZ_GEMM_SPLITK=0 disables, =N forces N splits of every tile of the tail.
-static void plan_units(GemmArgs& a, int cg, int tn, unsigned batch) {
+static void plan_units(GemmArgs& a, int cg, bool split3x, unsigned batch) {
     static const char* env = std::getenv("JZ_GEMM_SPLITK");
     static const int forced = env && *env ? std::atoi(env) : -1;
     const int num_kb = int(ceil_div(a.k, size_t(BK)));
@@ -271,7 +271,7 @@ static void plan_units(GemmArgs& a, int cg, int tn, unsigned batch) {
     if (batch > 1 || forced == 0 || forced == 1) return;
     const unsigned slots = unsigned(ctx().sm_count) / unsigned(cg);
     const unsigned rem = tiles % slots;
-    if (rem == 0) return;
+    if (rem == 0 || rem >= kTicketSlots / 2) return;
     constexpr int MIN_KB = 8;
     int S = forced > 1 ? forced : int(slots / rem);
     if (S > MAX_SPLITS) S = MAX_SPLITS;
@@ -282,10 +282,13 @@ static void plan_units(GemmArgs& a, int cg, int tn, unsigned batch) {
     if (kbs > kbc) kbs = ((kbs + kbc - 1) / kbc) * kbc;   // whole TMEM chunks per split
     S = (num_kb + kbs - 1) / kbs;
     if (S < 2) return;
+    // the fix-up (partial tile out through L2, ticket, slice back in) costs about as much as this many k-blocks of
+    // mainloop (a k-block is ~0.8 us in 3xTF32, ~0.27 us in TF32): split only when the tail gets shorter by more
+    const int fixup_kb = split3x ? 8 : 24;
+    if (forced <= 1 && num_kb - kbs <= fixup_kb) return;
     a.full_tiles = tiles - rem;
     a.splits = S;
     a.kb_per_split = kbs;
-    (void)tn;
 }
 
 static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
@@ -312,18 +315,22 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         pick_tile(m, n, cg, tn);
         args.tiles_m = unsigned(ceil_div(m, size_t(cg * TILE_M)));
         args.tiles_n = unsigned(ceil_div(n, size_t(tn)));
-        plan_units(args, cg, tn, batch);
+        plan_units(args, cg, split3x, batch);
+        if (args.splits == 1 && cg == 2 && tn == 256 && batch == 1 &&
+            size_t(args.tiles_m) * args.tiles_n * 2 <= size_t(ctx().sm_count) / 2) {
+            // a small grid that is not worth splitting along k: narrow tiles at least double the number of busy SM pairs
+            tn = 128;
+            args.tiles_n = unsigned(ceil_div(n, size_t(tn)));
+            plan_units(args, cg, split3x, batch);
+        }
         const unsigned split_tiles = args.tiles_m * args.tiles_n - args.full_tiles;
         if (split_tiles) {
-            const size_t ticket_bytes = (size_t(split_tiles) * sizeof(unsigned) + 511) & ~size_t(511);
-            const size_t part_bytes = size_t(split_tiles) * size_t(args.splits) * size_t(cg * TILE_M * tn) * sizeof(float);
-            rc = ws_alloc(&ws, ticket_bytes + part_bytes, s);
-            if (rc == JZ_OK) {
-                args.tickets = static_cast<unsigned*>(ws);
-                args.ws = reinterpret_cast<float*>(static_cast<char*>(ws) + ticket_bytes);
-                cudaError_t e = cudaMemsetAsync(ws, 0, ticket_bytes, s);
-                if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync(split-K tickets)");
-            }
+            // arrival / departure counters: [0, tiles) and [kTicketSlots/2, ...) of the per-stream ticket block
+            // (self-resetting, so no memset sits between two launches and programmatic dependent launch still applies)
+            args.tickets = tickets_for(s);
+            if (!args.tickets) rc = fail(JZ_ERR_CUDA, "gemm: could not allocate the ticket counters");
+            if (rc == JZ_OK) rc = ws_alloc(&ws, size_t(split_tiles) * size_t(args.splits) * size_t(cg * TILE_M * tn) * sizeof(float), s);
+            if (rc == JZ_OK) args.ws = static_cast<float*>(ws);
         }
         if (rc == JZ_OK) {
             for (unsigned b0 = 0; b0 < batch && rc == JZ_OK; b0 += 65535u) {   // grid.z limit

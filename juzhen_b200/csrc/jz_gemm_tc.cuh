@@ -77,7 +77,7 @@ struct GemmArgs {
     int kb_per_split;           // k-blocks per split unit
     int kb_per_chunk;           // k-blocks accumulated inside TMEM before promotion to registers
     float* ws;                  // split-K partial tiles: [split tile][split][rank][TN columns][128 rows]
-    unsigned* tickets;          // one per split tile, zeroed before the launch
+    unsigned* tickets;          // per-stream self-resetting counters: arrivals at [tile], departures at [kTicketSlots/2 + tile]
     int n_peers;                // additional destinations (peer-GPU images of C, same ldc)
     float* peers[JZ_MAX_PEERS];
     float* mc;                  // multicast (NVSwitch) image of C: when set, every element is stored by ONE multimem.st
@@ -556,6 +556,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else {
             // ---- k-split unit: park the raw partial tile, then finish a 1/splits column slice of the tile
             const int S = args.splits;
+            const unsigned want = unsigned(S) * CG;
             float* const ws_tile = args.ws + size_t(split_tile) * size_t(S) * (CG * TILE_ELEMS);   // [split][rank][col][row]
             {
                 float* dst = ws_tile + (size_t(split) * CG + rank) * TILE_ELEMS + size_t(half * HALF_N) * TILE_M + quarter * 32 + lane;
@@ -564,33 +565,84 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             __threadfence();
             epi_bar_sync();
+            unsigned* const tk = args.tickets + split_tile;
             if (te == 0) {
-                unsigned* tk = args.tickets + split_tile;
                 atomicAdd(tk, 1u);
-                const unsigned want = unsigned(S) * CG;
-                while (ld_acquire_gpu(tk) < want) __nanosleep(40);
+                while (ld_acquire_gpu(tk) < want) __nanosleep(20);
             }
             epi_bar_sync();
             __threadfence();
+            // slice: columns [c_begin, c_end) of this CTA's 128 rows; a thread owns 4 consecutive rows (128-bit loads of
+            // the partials, which sit [column][128 rows]) and every 8th column; the S partials are added in split
+            // order, UB columns (UB x S independent loads) at a time
             const int c_begin = split * TILE_N / S, c_end = (split + 1) * TILE_N / S;
-            const int r_local = te & (TILE_M - 1);
-            const size_t row = size_t(m0) + r_local;
-            if (row < args.m) {
-                for (int c = c_begin + (te >> 7); c < c_end; c += 2) {
-                    const size_t col = size_t(n0) + c;
-                    if (col >= args.n) break;
-                    const float* src = ws_tile + size_t(rank) * TILE_ELEMS + size_t(c) * TILE_M + r_local;
-                    float sum = __ldcg(src);
-                    for (int s = 1; s < S; s++) sum = __fadd_rn(sum, __ldcg(src + size_t(s) * (CG * TILE_ELEMS)));
-                    float v[1] = {args.alpha * sum};
-                    if (args.beta != 0.0f) v[0] += args.beta * Cb[row + col * ldc];
-                    if (s_chain.n) apply_chain<1>(v, s_chain);
-                    if (args.mc) {
-                        multimem_st(args.mc + row + col * ldc, v[0]);
-                    } else {
-                        Cb[row + col * ldc] = v[0];
-                        for (int d = 0; d < args.n_peers; d++) s_peers[d][row + col * ldc] = v[0];
+            const int r4 = (te & 31) * 4, cl = te >> 5;
+            const size_t row0 = size_t(m0) + r4;
+            const bool vec_ok = (ldc & 3) == 0 && aligned16(Cb) && row0 + 3 < args.m;
+            const float* const src0 = ws_tile + size_t(rank) * TILE_ELEMS + r4;
+            const size_t sstride = size_t(CG) * TILE_ELEMS;
+            constexpr int UB = 4;
+            for (int cb = c_begin + cl; cb < c_end; cb += 8 * UB) {
+                float4 a4[UB];
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    const int c = cb + 8 * u;
+                    a4[u] = c < c_end ? __ldcg(reinterpret_cast<const float4*>(src0 + size_t(c) * TILE_M)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll 2
+                for (int s = 1; s < S; s++) {
+                    float4 t4[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; u++) {
+                        const int c = cb + 8 * u;
+                        t4[u] = c < c_end ? __ldcg(reinterpret_cast<const float4*>(src0 + size_t(s) * sstride + size_t(c) * TILE_M))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+#pragma unroll
+                    for (int u = 0; u < UB; u++) {
+                        a4[u].x = __fadd_rn(a4[u].x, t4[u].x); a4[u].y = __fadd_rn(a4[u].y, t4[u].y);
+                        a4[u].z = __fadd_rn(a4[u].z, t4[u].z); a4[u].w = __fadd_rn(a4[u].w, t4[u].w);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    const int c = cb + 8 * u;
+                    const size_t col = size_t(n0) + c;
+                    if (c >= c_end || col >= args.n || row0 >= args.m) continue;
+                    float v[4] = {args.alpha * a4[u].x, args.alpha * a4[u].y, args.alpha * a4[u].z, args.alpha * a4[u].w};
+                    float* const dstc = Cb + row0 + col * ldc;
+                    if (args.beta != 0.0f) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (row0 + q < args.m) v[q] += args.beta * dstc[q];
+                    }
+                    if (s_chain.n) apply_chain<4>(v, s_chain);
+                    if (args.mc) {
+                        float* const dm = args.mc + row0 + col * ldc;
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (row0 + q < args.m) multimem_st(dm + q, v[q]);
+                    } else {
+                        for (int d = 0; d <= args.n_peers; d++) {
+                            float* const dd = (d == 0 ? Cb : s_peers[d - 1]) + row0 + col * ldc;
+                            if (vec_ok) {
+                                *reinterpret_cast<float4*>(dd) = make_float4(v[0], v[1], v[2], v[3]);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; q++)
+                                    if (row0 + q < args.m) dd[q] = v[q];
+                            }
+                        }
+                    }
+                }
+            }
+            // departure: the last CTA of the tile to get here leaves both counters at zero for the next launch
+            epi_bar_sync();
+            if (te == 0) {
+                unsigned* const dn = args.tickets + (kTicketSlots / 2) + split_tile;
+                if (atomicAdd(dn, 1u) == want - 1) {
+                    *tk = 0;
+                    *dn = 0;
                 }
             }
         }

@@ -491,24 +491,6 @@ __global__ void nrm2_final_kernel(float* out, const double* partial, int n) {
 }
 
 // ------------------------------------------------------------------ host dispatch
-// Zero-initialised ticket counters, one block per stream (kernels on a stream are serialised, and each launch
-// leaves its counters at zero again, so a block is never shared by two running kernels).
-constexpr size_t kTicketSlots = 4096;
-static unsigned* tickets_for(cudaStream_t s) {
-    static std::mutex mu;
-    static std::unordered_map<unsigned long long, unsigned*> blocks;   // key: (device, stream)
-    std::lock_guard<std::mutex> lock(mu);
-    const unsigned long long key = (unsigned long long)reinterpret_cast<uintptr_t>(s) * 64ull + (unsigned long long)(ctx().device & 63);
-    auto it = blocks.find(key);
-    if (it != blocks.end()) return it->second;
-    unsigned* p = nullptr;
-    if (cudaMalloc(&p, kTicketSlots * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    // zeroed on the SAME stream: ordered before the first kernel that uses it, whatever kind of stream s is
-    if (cudaMemsetAsync(p, 0, kTicketSlots * sizeof(unsigned), s) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
-    blocks[key] = p;
-    return p;
-}
-
 template <class Op>
 static int reduce_dim1(float* out, const float* a, size_t rows, size_t cols, size_t ld, cudaStream_t s);
 

@@ -199,6 +199,21 @@ static Pool& pool() {
     return *p;
 }
 
+unsigned* tickets_for(cudaStream_t s) {
+    static std::mutex mu;
+    static std::unordered_map<unsigned long long, unsigned*> blocks;   // key: (device, stream)
+    std::lock_guard<std::mutex> lock(mu);
+    const unsigned long long key = (unsigned long long)reinterpret_cast<uintptr_t>(s) * 64ull + (unsigned long long)(ctx().device & 63);
+    auto it = blocks.find(key);
+    if (it != blocks.end()) return it->second;
+    unsigned* p = nullptr;
+    if (cudaMalloc(&p, kTicketSlots * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // zeroed on the SAME stream: ordered before the first kernel that uses it, whatever kind of stream s is
+    if (cudaMemsetAsync(p, 0, kTicketSlots * sizeof(unsigned), s) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
+    blocks[key] = p;
+    return p;
+}
+
 int ws_alloc(void** p, size_t bytes, cudaStream_t s) { return pool().alloc(p, bytes, s); }
 int ws_free(void* p, cudaStream_t s) { return pool().release(p, s); }
 

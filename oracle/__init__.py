@@ -261,6 +261,17 @@ class Oracle:
         self._fn("rand")(c_uint(seed), _f(out), c_size_t(n))
         return out
 
+    def gemm_subblock(self, A, ta, B, tb, r0, r1, c0, c1):
+        """rows [r0, r1) x columns [c0, c1) of op(A)*op(B) via the reference's rows()/columns()/dot (reference build only)"""
+        A, B = _phys(A), _phys(B)
+        out = np.empty((r1 - r0, c1 - c0), dtype=np.float32, order="F")
+        rc = self._fn("gemm_subblock")(_f(A), c_size_t(A.shape[0]), c_size_t(A.shape[1]), c_int(ta),
+                                       _f(B), c_size_t(B.shape[0]), c_size_t(B.shape[1]), c_int(tb),
+                                       c_size_t(r0), c_size_t(r1), c_size_t(c0), c_size_t(c1), _f(out))
+        if rc == 2:
+            raise ValueError("Matrix dimensions are not compatible")
+        return out
+
     # ---- reference-only helpers
     def testbasic_expr(self, A, B):
         A, B = _phys(A), _phys(B)

@@ -188,6 +188,21 @@ int ref_gemm(const float* A, size_t ar, size_t ac, int ta, const float* B, size_
     return 0;
 }
 
+// Output sub-block rows [r0, r1) x columns [c0, c1) of op(A)*op(B), through the reference's own rows() / columns() /
+// dot (cpp/core.hpp:158-163, 393-410 -> cblas_sgemm): the OpenBLAS comparator BASELINE.md section 3 prescribes for
+// GEMM parity at sizes where the full CPU product takes minutes (2048 x 2048 block of a 16384^3 product: 137 GFLOP).
+int ref_gemm_subblock(const float* A, size_t ar, size_t ac, int ta, const float* B, size_t br, size_t bc, int tb,
+                      size_t r0, size_t r1, size_t c0, size_t c1, float* out) {
+    try {
+        const MF a = view(A, ar, ac, ta), b = view(B, br, bc, tb);
+        MF r = a.rows(r0, r1) * b.columns(c0, c1);
+        emit(r, out);
+    } catch (std::invalid_argument&) {
+        return 2;
+    }
+    return 0;
+}
+
 // the README / config-1 chain: log(exp(X)+1.0f)/5.0f  (README example)
 int ref_chain_softplus5(const float* in, float* out, size_t n) {
     const MF a = view(in, n, 1, 0);
