@@ -53,7 +53,8 @@ PROGRAMS = [
     ("benchmarkCoreOps", "tests/benchmarkCoreOps.cu", ["-DCUDNN_AVAILABLE", "-DJZ_LEGACY_CUBLAS_HANDLE", "-lcudnn", "-lcublas"]),
 ]
 # this repository's own C++ tests (same compute() convention), staged next to the reference's tests
-OWN_TESTS = [("test_fusion", "test_fusion.cu"), ("bench_attention", "bench_attention.cu"), ("bench_overhead", "bench_overhead.cu")]
+OWN_TESTS = [("test_fusion", "test_fusion.cu", []), ("bench_attention", "bench_attention.cu", ["-lcublas"]),
+             ("bench_overhead", "bench_overhead.cu", []), ("bench_mnist_step", "bench_mnist_step.cu", [])]
 OURS_IN_CPP = {"cumatrix.cuh", "memory.hpp", "jz_lazy.hpp"}
 REF_CPP = ["core.hpp", "matrix.hpp", "operators.hpp", "helper.hpp", "juzhen.hpp", "cpulinalg.hpp"]
 
@@ -81,7 +82,7 @@ def stage():
         for p in glob.glob(os.path.join(REF, sub, "*")):
             if os.path.isfile(p):
                 link(p, os.path.join(STAGE, sub, os.path.basename(p)))
-    for _, src in OWN_TESTS:
+    for _, src, _x in OWN_TESTS:
         link(os.path.join(HERE, "tests", src), os.path.join(STAGE, "tests", src))
     link(os.path.join(REF, "external", "xpu_info", "xpu_info.hpp"), os.path.join(STAGE, "external", "xpu_info", "xpu_info.hpp"))
     eig = os.path.join(REF, "external", "Eigen3")
@@ -163,7 +164,7 @@ def build(only=None, force=False):
         run([NVCC, *fl, *extra, os.path.join(STAGE, src), *use, *link_flags, "-o", exe], f"build {name}")
         return name, "built"
 
-    todo = [p for p in PROGRAMS + [(n, "tests/" + s, []) for n, s in OWN_TESTS] if not only or p[0] in only]
+    todo = [p for p in PROGRAMS + [(n, "tests/" + s, x) for n, s, x in OWN_TESTS] if not only or p[0] in only]
     with concurrent.futures.ThreadPoolExecutor(max_workers=6) as ex:
         res = list(ex.map(one, todo))
     for name, st in res:

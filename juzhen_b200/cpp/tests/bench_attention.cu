@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <vector>
 
+#include <cublas_v2.h>   // comparison bar only: the library call the reference makes (ml/layer.hpp:2896-2926)
+
 #include "../cpp/juzhen.hpp"
 #include "../ml/layer.hpp"
 
@@ -60,6 +62,50 @@ int compute() {
         report("softmax rows backward", S, B, 12.0 * n, t0, t1, df);
         bad += df > 1e-4;
         for (float* p : {x, y0, y1, d, g0, g1}) cudaFree(p);
+    }
+    // ---- the two strided-batched products of TransformerLayer's attention (ml/layer.hpp:2896-2926), one head's worth:
+    //      scores = scale * Q^T K   (op T, N: m = n = seq, k = d_h, lda = ldb = d_k)   and   H = V A^T (op N, T: m = d_h, n = k = seq)
+    //      jz_gemm_strided_batched (3xTF32 = fp32 accuracy, and TF32) against cublasSgemmStridedBatched in its default
+    //      fp32 math (what the reference runs) and with TF32 tensor-op math (NVIDIA_TF32=1)
+    {
+        cublasHandle_t h;
+        cublasCreate(&h);
+        const size_t gcases[][3] = {{64, 128, 2048}, {128, 128, 1024}, {256, 128, 512}, {512, 128, 128}, {1024, 128, 32}, {256, 64, 512}};   // seq, d_h, batch
+        for (auto& c : gcases) {
+            const size_t S = c[0], DH = c[1], B = c[2], DK = DH;   // one head: d_k = d_h
+            const size_t nq = DK * S * B, ns = S * S * B;
+            float *q = dalloc(nq, 21), *k = dalloc(nq, 22), *v = dalloc(nq, 23), *s0 = dalloc(ns, 24), *s1 = dalloc(ns, 25), *h0 = dalloc(nq, 26), *h1 = dalloc(nq, 27);
+            const float scale = 1.0f / std::sqrt((float)DH), zero = 0.0f, one = 1.0f;
+            const double fl = 2.0 * S * S * DH * B;
+            for (int pass = 0; pass < 2; pass++) {   // 0: QK^T, 1: V A^T
+                auto cublas_call = [&] {
+                    if (pass == 0) cublasSgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, (int)S, (int)S, (int)DH, &scale, q, (int)DK, (long long)(DK * S), k, (int)DK,
+                                                             (long long)(DK * S), &zero, s0, (int)S, (long long)(S * S), (int)B);
+                    else cublasSgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)DH, (int)S, (int)S, &one, v, (int)DK, (long long)(DK * S), s0, (int)S,
+                                                   (long long)(S * S), &zero, h0, (int)DK, (long long)(DK * S), (int)B);
+                };
+                auto ours_call = [&](int mode) {
+                    if (pass == 0) jz_gemm_strided_batched(1, 0, S, S, DH, scale, q, DK, DK * S, k, DK, DK * S, 0.0f, s1, S, S * S, B, mode, nullptr);
+                    else jz_gemm_strided_batched(0, 1, DH, S, S, 1.0f, v, DK, DK * S, s0, S, S * S, 0.0f, h1, DK, DK * S, B, mode, nullptr);
+                };
+                cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
+                const double t_fp32 = time_ms(cublas_call, 20);
+                cublasSetMathMode(h, CUBLAS_TF32_TENSOR_OP_MATH);
+                const double t_tf32 = time_ms(cublas_call, 20);
+                cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
+                cublas_call();   // fp32 result as the comparator
+                const double t_3x = time_ms([&] { ours_call(0); }, 20);
+                const int path = jz_gemm_last_path();
+                const double df = pass == 0 ? max_diff(s0, s1, ns) : max_diff(h0, h1, nq);
+                const double t_1x = time_ms([&] { ours_call(1); }, 20);
+                std::printf("batched gemm %-6s seq %4zu d_h %3zu batch %4zu | cuBLAS fp32 %7.3f ms %6.1f TF | cuBLAS TF32 %7.3f ms %6.1f TF | juzhen-b200 3xTF32 %7.3f ms %6.1f TF (x%.1f vs fp32, path %d, max|diff| %.1e) | TF32 %7.3f ms %6.1f TF (x%.2f vs cuBLAS TF32)\n",
+                            pass == 0 ? "Q^T K" : "V A^T", S, DH, B, t_fp32, fl / t_fp32 / 1e9, t_tf32, fl / t_tf32 / 1e9, t_3x, fl / t_3x / 1e9, t_fp32 / t_3x, path, df,
+                            t_1x, fl / t_1x / 1e9, t_tf32 / t_1x);
+                bad += df > 1e-3 * std::sqrt((double)(pass == 0 ? DH : S));
+            }
+            for (float* p : {q, k, v, s0, s1, h0, h1}) cudaFree(p);
+        }
+        cublasDestroy(h);
     }
     const size_t ln[][2] = {{256, 65536}, {512, 32768}, {1024, 16384}, {4096, 4096}};   // (dim, tokens)
     for (auto& c : ln) {

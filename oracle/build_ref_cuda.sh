@@ -24,4 +24,14 @@ wait
 # the reference's operator benchmark (tests/benchmarkCoreOps.cu: GEMM 512^3, cuDNN conv, LayerNorm, attention block, Adam)
 [ "$OUT/benchmarkCoreOps" -nt "$OUT/cumatrix.o" ] || nvcc $FLAGS -DCUDNN_AVAILABLE "$REF/tests/benchmarkCoreOps.cu" "$OUT/launcher.o" "$OUT/cumatrix.o" "$OUT/cukernels.o" \
     -lcublas -lcurand -lcudnn "$OB" -Xlinker --disable-new-dtags -Xlinker -rpath -Xlinker "$(dirname "$OB")" -lpthread -o "$OUT/benchmarkCoreOps"
+# this repository's demo_mnist-step benchmark (juzhen_b200/cpp/tests/bench_mnist_step.cu: the loop body of examples/demo_mnist.cu
+# at a batch size from the environment) against the reference's own CUDA sources: staged by symlink so that its
+# `#include "../cpp/juzhen.hpp"` resolves into the reference tree
+STAGE=$OUT/stage
+mkdir -p "$STAGE/tests"
+ln -sfn "$REF/cpp" "$STAGE/cpp"; ln -sfn "$REF/ml" "$STAGE/ml"; ln -sfn "$REF/external" "$STAGE/external"
+ln -sfn "$HERE/../juzhen_b200/cpp/tests/bench_mnist_step.cu" "$STAGE/tests/bench_mnist_step.cu"
+[ "$OUT/bench_mnist_step" -nt "$HERE/../juzhen_b200/cpp/tests/bench_mnist_step.cu" ] && [ "$OUT/bench_mnist_step" -nt "$OUT/cumatrix.o" ] || \
+  nvcc $FLAGS "$STAGE/tests/bench_mnist_step.cu" "$OUT/launcher.o" "$OUT/cumatrix.o" "$OUT/cukernels.o" \
+      -lcublas -lcurand "$OB" -Xlinker --disable-new-dtags -Xlinker -rpath -Xlinker "$(dirname "$OB")" -lpthread -o "$OUT/bench_mnist_step"
 ls -la "$OUT" | grep -v "\.o$"

@@ -39,9 +39,9 @@ for stage in "$@"; do
       timeout -k 5 600 build/dropin/bin/bench_attention 2>&1 | grep -v "^profiler\|^GPU\|^Juzhen\|^___\|^GEMM mode" | tee gpurun_out/${TAG}_attention.log ;;
     mnist)
       for b in 32 8192 60000; do
-        echo "--- batch $b: juzhen-b200"; JZ_STATS=1 timeout -k 5 300 build/dropin/bin/bench_mnist_step $b 2>&1 | grep -E "bench_mnist_step|jz_stats"
-        echo "--- batch $b: reference CUDA/cuBLAS build"; timeout -k 5 300 oracle/_ref/cuda/bench_mnist_step $b 2>&1 | grep -E "bench_mnist_step"
-        echo "--- batch $b: reference CUDA/cuBLAS build, NVIDIA_TF32=1"; NVIDIA_TF32=1 timeout -k 5 300 oracle/_ref/cuda/bench_mnist_step $b 2>&1 | grep -E "bench_mnist_step"
+        echo "--- batch $b: juzhen-b200"; MNIST_BATCH=$b JZ_STATS=1 timeout -k 5 300 build/dropin/bin/bench_mnist_step 2>&1 | grep -E "bench_mnist_step|jz_stats"
+        echo "--- batch $b: reference CUDA/cuBLAS build"; MNIST_BATCH=$b timeout -k 5 300 oracle/_ref/cuda/bench_mnist_step 2>&1 | grep -E "bench_mnist_step"
+        echo "--- batch $b: reference CUDA/cuBLAS build, NVIDIA_TF32=1"; NVIDIA_TF32=1 MNIST_BATCH=$b timeout -k 5 300 oracle/_ref/cuda/bench_mnist_step 2>&1 | grep -E "bench_mnist_step"
       done 2>&1 | tee gpurun_out/${TAG}_mnist_step.log ;;
     ncu_gemm)
       timeout -k 5 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 6 -c 12 -o gpurun_out/${TAG}_gemm -f \
