@@ -11,11 +11,15 @@ divided by the device time of the step, in GB/s, summed over all ranks (weak sca
 GPU runs the same per-GPU batch, the path shards by independent elements, no collective).
 `e2e` is the same step driven through the C-ABI with HOST buffers: the inputs are copied from
 pinned host memory and the reduction results are read back inside the timed region.
-`gemm` carries the TFLOP/s half of the metric (fp32 GEMM, 3xTF32 and TF32 modes).
+The other BASELINE configs ride in the same line: `gemm` = configs[2] (fp32 GEMM 1024..16384, A*B / A.T*B / A*B.T,
+3xTF32 and TF32 modes, TFLOP/s and fraction of the tensor roofline), `config1` = configs[0] (4096^2 A*B then
+log(exp(A*B/4096)+1)/5: fused epilogue vs separate passes, checked against the reference's CPU result),
+`mnist_step` = configs[3] (demo_mnist step at batch 32 / 8192 / 60000, this backend and the reference's CUDA build),
+`sharded_gemm` = configs[4] (32768^3 column-sharded GEMM + fused chain: the N = 1 anchor here, strong scaling at N > 1).
 
 --impl reference times the reference's own CPU implementation of the same step
 (oracle/_ref/libjzref.so = the unmodified Matrix<float> + OpenBLAS build; falls back to the
-pinned C restatement when that file did not travel) on a bounded sample of the batch.
+pinned C restatement when that file did not travel) on the SAME workload (one full 2^28 step), all host threads.
 """
 from __future__ import annotations
 
@@ -286,26 +290,30 @@ def run_ours(args):
            "cpu_affinity": numa,
            "h2d_GB/s": round(2 * 4 * sw.n / (ms_e2e * 1e-3) / 1e9, 1)}
 
-    # ---- GEMM half of the metric
+    # ---- GEMM half of the metric (BASELINE configs[2]): n x {A*B, A.T*B, A*B.T} x {3xTF32, TF32}
     gemm = {}
     if not args.no_gemm:
         for gn in args.gemm_n:
             a, b = jz.CM.randn(gn, gn, seed=11), jz.CM.randn(gn, gn, seed=12)
             c = jz.CM.empty("c", gn, gn)
-            for mode_name, mode in (("3xtf32", 0), ("tf32", 1)):
-                def g():
-                    rc = L.jz_gemm(0, 0, gn, gn, gn, 1.0, a.ptr, gn, b.ptr, gn, 0.0, c.ptr, gn, mode, stream)
-                    if rc:
-                        raise RuntimeError(L.jz_last_error().decode())
-                try:
-                    ms, _ = timed(g, max(3, args.steps // 2), 2)
-                except RuntimeError as e:
-                    gemm[f"{mode_name}_{gn}"] = {"error": str(e)}
-                    continue
-                tf = 2.0 * gn ** 3 / (ms * 1e-3) / 1e12 * world
-                peak = pk["bf16_tflops"] / 2 / (3 if mode == 0 else 1)   # TF32 = bf16/2; 3xTF32 = TF32/3
-                gemm[f"{mode_name}_{gn}"] = {"TFLOP/s": round(tf, 1), "ms": round(ms, 3), "roofline_peak": round(peak * world, 1),
-                                             "frac": round(tf / (peak * world), 3), "path": L.jz_gemm_last_path()}
+            reps = max(3, args.steps // 2) if gn >= 8192 else max(10, args.steps)
+            for ta, tb, suffix in ((0, 0, ""), (1, 0, "_ATB"), (0, 1, "_ABT")):
+                for mode_name, mode in (("3xtf32", 0), ("tf32", 1)):
+                    def g():
+                        rc = L.jz_gemm(ta, tb, gn, gn, gn, 1.0, a.ptr, gn, b.ptr, gn, 0.0, c.ptr, gn, mode, stream)
+                        if rc:
+                            raise RuntimeError(L.jz_last_error().decode())
+                    key = f"{mode_name}_{gn}{suffix}"
+                    try:
+                        ms, _ = timed(g, reps, 3)
+                    except RuntimeError as e:
+                        gemm[key] = {"error": str(e)}
+                        continue
+                    tf = 2.0 * gn ** 3 / (ms * 1e-3) / 1e12 * world
+                    peak = pk["bf16_tflops"] / 2 / (3 if mode == 0 else 1)   # TF32 = bf16/2; 3xTF32 = TF32/3
+                    gemm[key] = {"TFLOP/s": round(tf, 1), "ms": round(ms, 4), "roofline_peak": round(peak * world, 1),
+                                 "frac": round(tf / (peak * world), 3), "path": L.jz_gemm_last_path(),
+                                 "k_splits_of_tail_tiles": L.jz_gemm_last_splits()}
             del a, b, c
             # measurement only (never on the product path): what the vendor library reaches on this box for the same
             # product, as a cross-check of the assumed TF32 peak (MEASURED_PEAKS.json has no TF32 figure)
@@ -314,20 +322,27 @@ def run_ours(args):
                 ta_, tb_ = torch.randn(gn, gn, device="cuda"), torch.randn(gn, gn, device="cuda")
                 for allow, key in ((True, "cublas_tf32"), (False, "cublas_fp32")):
                     torch.backends.cuda.matmul.allow_tf32 = allow
-                    ms, _ = timed(lambda: torch.matmul(ta_, tb_), max(3, args.steps // 2), 2)
-                    gemm[f"{key}_{gn}"] = {"TFLOP/s": round(2.0 * gn ** 3 / (ms * 1e-3) / 1e12 * world, 1), "ms": round(ms, 3),
+                    ms, _ = timed(lambda: torch.matmul(ta_, tb_), reps if allow else max(3, reps // 3), 2)
+                    gemm[f"{key}_{gn}"] = {"TFLOP/s": round(2.0 * gn ** 3 / (ms * 1e-3) / 1e12 * world, 1), "ms": round(ms, 4),
                                            "note": "torch.matmul (cuBLAS) on the same box: comparison bar, not our kernel"}
                 torch.backends.cuda.matmul.allow_tf32 = old
                 del ta_, tb_
             except Exception as e:  # noqa: BLE001
                 gemm[f"cublas_{gn}"] = {"error": str(e)[:120]}
 
+    config1 = None
+    if rank == 0 and world == 1 and not args.no_gemm:
+        try:
+            config1 = run_config1(jz, L, stream, timed, pk, no_cpu=args.no_cpu)
+        except Exception as e:  # noqa: BLE001
+            config1 = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     clk = clocks.stop() if rank == 0 else None   # sampled across every timed region above (sweep, per-op, e2e, GEMM)
     sharded = None
     sharded_sum = None
     if world > 1:
         sharded_sum = run_sharded_colsum(jz, L, sw, world, stream, timed, pk)
-    if world > 1 and not args.no_gemm:
+    if not args.no_gemm:   # N = 1 runs the same product whole: the anchor of the strong-scaling curve
         sharded = run_sharded_gemm(jz, L, args, world, rank, stream, timed, pk)
 
     cpu = None
@@ -351,7 +366,7 @@ def run_ours(args):
                        "algorithmic_bytes_per_step": sw.bytes_per_step, "parallelism": f"independent shards x{world}"},
             "frac_of_hbm_peak": round(value / world / pk["hbm_gbs"], 3),
             "frac_of_8TBs_spec": round(value / world / 8000.0, 3),
-            "roofline": roofline, "ops": per_op, "gemm": gemm, "sharded_gemm": sharded, "sharded_colsum": sharded_sum, "mnist_step": mnist, "e2e": e2e,
+            "roofline": roofline, "ops": per_op, "gemm": gemm, "config1": config1, "sharded_gemm": sharded, "sharded_colsum": sharded_sum, "mnist_step": mnist, "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk, "cpu_baseline": cpu,
         }
@@ -382,68 +397,159 @@ def run_sharded_colsum(jz, L, sw, world, stream, timed, pk):
             "GB/s_aggregate": round(gbs, 1), "frac_of_hbm_peak_xN": round(gbs / (pk["hbm_gbs"] * world), 3)}
 
 
+def run_config1(jz, L, stream, timed, pk, no_cpu=False):
+    """BASELINE configs[0]: 4096 x 4096 fp32 A*B then log(exp(A*B/4096)+1)/5 (examples/demo_gemm.cu:41-95 style; the
+    1/4096 keeps exp finite).  Three spellings on the GPU -- the chain fused into the GEMM
+    epilogue (1 launch), GEMM + one fused elementwise pass (2 launches), GEMM + the five separate maps an
+    lvalue-by-lvalue operator chain issues (6 launches) -- and the reference's own CPU result (Matrix<float>, OpenBLAS)
+    on the same inputs as the comparator and the CPU bar."""
+    import numpy as np
+    n = 4096
+    rng = np.random.default_rng(41)
+    A = np.asfortranarray(rng.standard_normal((n, n), dtype=np.float32))
+    B = np.asfortranarray(rng.standard_normal((n, n), dtype=np.float32))
+    a, b = jz.CM(A), jz.CM(B)
+    cf, cs, c5 = jz.CM.empty("cf", n, n), jz.CM.empty("cs", n, n), jz.CM.empty("c5", n, n)
+    inv_n = float(np.float32(1.0 / n))
+    steps, ns = jz._lib.make_steps([("affine", inv_n, 0.0), ("exp",), ("affine", 1.0, 1.0), ("log",), ("affine", FIFTH, 0.0)])
+    U, nn = jz._lib.UNARY, n * n
+
+    def ck(rc):
+        if rc:
+            raise RuntimeError(L.jz_last_error().decode())
+
+    def fused():
+        ck(L.jz_gemm_chain(0, 0, n, n, n, 1.0, a.ptr, n, b.ptr, n, cf.ptr, n, steps, ns, 0, stream))
+
+    def gemm_then_chain():
+        ck(L.jz_gemm(0, 0, n, n, n, 1.0, a.ptr, n, b.ptr, n, 0.0, cs.ptr, n, 0, stream))
+        ck(L.jz_chain(cs.ptr, cs.ptr, nn, steps, ns, stream))
+
+    def gemm_then_maps():
+        ck(L.jz_gemm(0, 0, n, n, n, 1.0, a.ptr, n, b.ptr, n, 0.0, c5.ptr, n, 0, stream))
+        ck(L.jz_affine(c5.ptr, c5.ptr, nn, inv_n, 0.0, stream))
+        ck(L.jz_unary(U["exp"], c5.ptr, c5.ptr, nn, stream))
+        ck(L.jz_affine(c5.ptr, c5.ptr, nn, 1.0, 1.0, stream))
+        ck(L.jz_unary(U["log"], c5.ptr, c5.ptr, nn, stream))
+        ck(L.jz_affine(c5.ptr, c5.ptr, nn, FIFTH, 0.0, stream))
+
+    out = {"workload": "BASELINE configs[0]: 4096^2 fp32 A*B then log(exp(A*B/4096)+1)/5, 3xTF32 (fp32 accuracy)"}
+    peak = pk["bf16_tflops"] / 2 / 3
+    for name, fn in (("fused_epilogue_1_launch", fused), ("gemm_plus_fused_chain_2_launches", gemm_then_chain),
+                     ("gemm_plus_5_maps_6_launches", gemm_then_maps)):
+        ms, _ = timed(fn, 10, 3)
+        tf = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
+        out[name] = {"ms": round(ms, 4), "TFLOP/s": round(tf, 1), "frac_of_3xtf32_roofline": round(tf / peak, 3)}
+    hf, hs, h5 = cf.to_host(), cs.to_host(), c5.to_host()
+    out["fused_equals_separate_bitwise"] = bool(np.array_equal(hf.view(np.uint32), hs.view(np.uint32)) and
+                                                np.array_equal(hf.view(np.uint32), h5.view(np.uint32)))
+    if not no_cpu:
+        res = cpu_task("config1", {"A": A, "B": B})
+        if "error" in res:
+            out["reference_cpu"] = res
+        else:
+            outp = res.pop("out")
+            want = np.load(outp)
+            out["rel_fro_vs_reference_cpu"] = float(f"{np.linalg.norm(hf.astype(np.float64) - want) / np.linalg.norm(want):.3e}")
+            out["reference_cpu"] = res
+            _rm_tmp(outp)
+    return out
+
+
 def run_sharded_gemm(jz, L, args, world, rank, stream, timed, pk):
-    """BASELINE configs[4]: column-sharded C = log(exp(A*B/n)+1)/5 with the chain fused in the GEMM epilogue,
-    gathered (a) by one NCCL all-gather, (b) by P2P stores from the epilogue (fused) -- strong scaling."""
+    """BASELINE configs[4]: column-sharded C = log(exp(A*B/n)+1)/5 (3xTF32) with the chain fused in the GEMM epilogue,
+    STRONG scaling: the same n^3 product over N GPUs.  N = 1 runs it whole (the anchor).  N > 1 gathers the blocks by
+    (a) one NCCL all-gather, (b) P2P stores from the epilogue, (c) multimem.st to the NVSwitch multicast mapping,
+    (d) the torch-free jz_mg_* ABI (CUDA IPC).  Parity: replicas identical, all modes the same bits, 64 sampled entries
+    per rank against float64, and on rank 0 a 256 x 256 sub-block against the reference's CPU path (oracle/_ref)."""
+    import numpy as np
     import torch
     import torch.distributed as dist
     from juzhen_b200 import mg
     out = {}
+    modes = ("nccl", "fused", "mcast", "ipc") if world > 1 else ("local",)
     for n in args.sharded_n:
         steps = [("affine", 1.0 / n, 0.0), ("exp",), ("affine", 1.0, 1.0), ("log",), ("affine", FIFTH, 0.0)]
-        a = jz.CM.randn(n, n, seed=21)                       # replicated operand (same seed on every rank)
+        a = jz.CM.randn(n, n, seed=21)        # replicated operands: the same bits on every rank (same seed, same stream id)
+        bfull = jz.CM.randn(n, n, seed=22)
         j0, j1 = mg.block_range(n, world, rank)
-        bfull_seed = 22
-        b = jz.CM.randn(n, j1 - j0, seed=bfull_seed, offset=j0 * n)   # this rank's column block of the same B
-        res = {}
+        b_ptr = bfull.ptr + 4 * j0 * n         # this rank's column block: contiguous in column-major storage
+        res = {"strong_scaling": True, "flops": 2.0 * n ** 3}
         sums = {}
-        for mode in ("nccl", "fused"):
+        peak = pk["bf16_tflops"] / 2 / 3 * world
+        c_keep = None
+        for mode in modes:
             try:
                 g = mg.GpuShardedGemm(jz, n, n, n, steps=steps, gemm_mode=0, mode=mode)
-                fn = lambda: g.run(a.ptr, n, 0, b.ptr, n, stream)  # noqa: E731
-                ms, _ = timed(fn, max(2, args.steps // 3), 1)
+                fn = lambda: g.run(a.ptr, n, 0, b_ptr, n, stream)  # noqa: E731
+                ms, _ = timed(fn, max(3, args.steps // 3), 2)
             except Exception as e:  # noqa: BLE001 - report, keep the bench line alive
                 res[mode] = {"error": f"{type(e).__name__}: {e}"[:300]}
                 continue
             tf = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
-            peak = pk["bf16_tflops"] / 2 / 3 * world
             chk = g.c_full.view(torch.int32).sum(dtype=torch.int64)
             lo, hi = chk.clone(), chk.clone()
-            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if world > 1:
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             sums[mode] = int(chk.item())
             res[mode] = {"ms": round(ms, 3), "TFLOP/s": round(tf, 1), "frac_of_3xtf32_peak_xN": round(tf / peak, 3),
                          "replicas_identical": bool(lo.item() == hi.item())}
+            if c_keep is None:
+                c_keep = g.c_full.clone() if (n <= 16384 or world == 1) else g.c_full   # for the parity checks below
+            g.close()
             del g
             torch.cuda.empty_cache()
-        if len(sums) == 2:
-            res["fused_equals_nccl_bitwise"] = sums["nccl"] == sums["fused"]
-        # truth check at full size: 64 entries of this rank's column block recomputed in float64 on the device
+        ok_modes = [m for m in modes if m in sums]
+        if len(ok_modes) > 1:
+            res["all_modes_same_bits"] = len({sums[m] for m in ok_modes}) == 1
+        if ok_modes:
+            best = min(ok_modes, key=lambda m: res[m]["ms"])
+            res["best"] = {"mode": best, **res[best]}
+        # truth checks at full size on the gathered C of the first mode that ran
         try:
             gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
             ii = torch.randint(0, n, (64,), generator=gen).cuda()
-            jj = torch.randint(j0, j1, (64,), generator=gen).cuda()
+            jj = torch.randint(0, n, (64,), generator=gen).cuda()     # any column: other ranks' blocks included
             A2 = torch.empty(n * n, dtype=torch.float32, device="cuda")
             L.jz_copy(A2.data_ptr(), a.ptr, n * n, stream)
-            B2 = torch.empty(n * (j1 - j0), dtype=torch.float32, device="cuda")
-            L.jz_copy(B2.data_ptr(), b.ptr, n * (j1 - j0), stream)
+            B2 = torch.empty(n * n, dtype=torch.float32, device="cuda")
+            L.jz_copy(B2.data_ptr(), bfull.ptr, n * n, stream)
             Arows = A2.view(n, n).t()[ii, :].double()                    # logical A[i, :] of the column-major buffer
-            Bcols = B2.view(j1 - j0, n)[jj - j0, :].double()             # logical B[:, j]
+            Bcols = B2.view(n, n)[jj, :].double()                        # logical B[:, j]
             x = (Arows * Bcols).sum(dim=1) / n
             want = torch.log(torch.exp(x) + 1.0) / 5.0
-            g2 = mg.GpuShardedGemm(jz, n, n, n, steps=steps, gemm_mode=0, mode="nccl")
-            cf = g2.run(a.ptr, n, 0, b.ptr, n, stream)
-            got = cf.view(n, n).t()[ii, jj].double()
+            got = c_keep.view(n, n).t()[ii, jj].double()
             rel = float((got - want).norm() / want.norm())
             worst = torch.tensor([rel], device="cuda", dtype=torch.float64)
-            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            if world > 1:
+                dist.all_reduce(worst, op=dist.ReduceOp.MAX)
             res["rel_err_64_sampled_entries_per_rank_vs_float64"] = float(f"{worst.item():.3e}")
-            del A2, B2, g2, cf
-            torch.cuda.empty_cache()
+            if rank == 0 and not args.no_cpu:
+                # 256 x 256 sub-block straddling a block boundary when there is one, against the reference's CPU path
+                blk = 256
+                r0 = (n // 3) // 4 * 4
+                c0 = max(0, min(n - blk, (n // world if world > 1 else n // 2) - blk // 2))
+                Ah = A2.view(n, n).t()[r0:r0 + blk, :].contiguous().cpu().numpy()          # (blk, n) C-order
+                Bh = B2.view(n, n)[c0:c0 + blk, :].contiguous().cpu().numpy()              # (blk, n): rows = columns of B
+                sub = cpu_task("gemm_chain_block", {"Arows": np.asfortranarray(Ah), "Bcols": np.asfortranarray(Bh.T), "n": np.array([n])})
+                if "error" in sub:
+                    res["subblock_vs_reference_cpu"] = sub
+                else:
+                    outp = sub.pop("out")
+                    want_blk = np.load(outp)
+                    _rm_tmp(outp)
+                    got_blk = c_keep.view(n, n).t()[r0:r0 + blk, c0:c0 + blk].cpu().numpy()
+                    sub["rel_fro"] = float(f"{np.linalg.norm(got_blk.astype(np.float64) - want_blk) / np.linalg.norm(want_blk):.3e}")
+                    sub["block"] = f"rows [{r0}, {r0 + blk}) x columns [{c0}, {c0 + blk})"
+                    res["subblock_vs_reference_cpu"] = sub
+            del A2, B2
         except Exception as e:  # noqa: BLE001
-            res["sampled_check_error"] = f"{type(e).__name__}: {e}"[:200]
+            res["parity_check_error"] = f"{type(e).__name__}: {e}"[:200]
+        c_keep = None
+        torch.cuda.empty_cache()
         out[str(n)] = res
-        del a, b
+        del a, bfull
     return out
 
 
@@ -494,6 +600,41 @@ def mnist_step_block():
             blk["speedup_vs_reference_cuda"] = round(blk["reference_cuda_cublas"]["ms_per_step"] / blk["ours"]["ms_per_step"], 2)
         except (KeyError, ZeroDivisionError):
             pass
+    # the same training step at batch 32 / 8192 / 60000: juzhen_b200/cpp/tests/
+    # bench_mnist_step.cu = the loop body of the demo on synthetic MNIST-shaped data, CUDA events, built against this
+    # backend and against the reference's CUDA/cuBLAS sources (fp32 math, and NVIDIA_TF32=1)
+    ours_b = os.path.join(ROOT, "build", "dropin", "bin", "bench_mnist_step")
+    ref_b = os.path.join(ROOT, "oracle", "_ref", "cuda", "bench_mnist_step")
+
+    def one(binary, batch, env_extra):
+        if not os.path.exists(binary):
+            return None
+        env = dict(os.environ, MNIST_BATCH=str(batch), **env_extra)
+        try:
+            r = subprocess.run([binary], cwd=proj, env=env, capture_output=True, text=True, timeout=240)
+        except (OSError, subprocess.TimeoutExpired) as e:
+            return {"error": str(e)[:120]}
+        res = {}
+        for ln in r.stdout.splitlines():
+            if ln.startswith("bench_mnist_step"):
+                for tok in ln.split()[1:]:
+                    k, _, v = tok.partition("=")
+                    res[k] = float(v) if k != "batch" and k != "steps" else int(v)
+            if "jz_stats" in ln and "kernel launches" in ln and "steps" in res:
+                res["launches_per_step"] = round(int(ln.split("ms,")[1].split("kernel")[0]) / res["steps"], 1)
+        return res or {"error": (r.stderr or r.stdout)[-200:]}
+
+    batches = {}
+    for batch in (32, 8192, 60000):
+        row = {"ours_3xtf32": one(ours_b, batch, {"JZ_STATS": "1"}), "ours_tf32": one(ours_b, batch, {"NVIDIA_TF32": "1"}),
+               "reference_cuda_fp32": one(ref_b, batch, {}), "reference_cuda_tf32": one(ref_b, batch, {"NVIDIA_TF32": "1"})}
+        try:
+            row["speedup_fp32_accuracy"] = round(row["reference_cuda_fp32"]["ms_per_step"] / row["ours_3xtf32"]["ms_per_step"], 2)
+            row["speedup_tf32"] = round(row["reference_cuda_tf32"]["ms_per_step"] / row["ours_tf32"]["ms_per_step"], 2)
+        except (KeyError, TypeError, ZeroDivisionError):
+            pass
+        batches[str(batch)] = row
+    blk["step_by_batch"] = batches
     return blk
 
 
@@ -566,23 +707,88 @@ def run_cpu(log2n, steps, warmup):
     return out
 
 
+def _cpu_env():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU bar is 'all host cores' (OpenBLAS threads)"""
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "GOTO_NUM_THREADS", "MKL_NUM_THREADS"):
+        env.pop(k, None)
+    return env
+
+
 def cpu_reference_subprocess(log2n, steps, warmup=0):
     """run in a child so the reference's exit-time profiler printouts cannot pollute our JSON line"""
     r = subprocess.run([sys.executable, os.path.abspath(__file__), "--_cpu_child", "--cpu-log2n", str(log2n),
-                        "--steps", str(steps), "--warmup", str(warmup)], capture_output=True, text=True, timeout=900)
+                        "--steps", str(steps), "--warmup", str(warmup)], capture_output=True, text=True, timeout=1500, env=_cpu_env())
     for ln in r.stdout.splitlines():
         if ln.startswith("{"):
             return json.loads(ln)
     return {"error": (r.stderr or r.stdout)[-400:]}
 
 
+def _rm_tmp(outp):
+    import shutil
+    shutil.rmtree(os.path.dirname(outp), ignore_errors=True)
+
+
+def cpu_task(task, arrays):
+    """one-off CPU-reference computation in a child process (oracle/_ref when it travelled, else the C restatement):
+    inputs through an .npz, the result through an .npy whose path comes back as res['out']"""
+    import tempfile
+    import numpy as np
+    d = tempfile.mkdtemp(prefix="jz_cpu_")
+    inp = os.path.join(d, "in.npz")
+    np.savez(inp, **arrays)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--_cpu_child", "--_cpu_task", task, "--_cpu_io", inp],
+                       capture_output=True, text=True, timeout=1500, env=_cpu_env())
+    for ln in r.stdout.splitlines():
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return {"error": (r.stderr or r.stdout)[-400:]}
+
+
+def run_cpu_task(task, inp):
+    import numpy as np
+    import oracle
+    O, kind = (oracle.ref(), "reference") if oracle.ref_available() else (oracle.port(), "port")
+    z = np.load(inp)
+    outp = inp[:-4] + ".out.npy"
+    threads = O.blas_threads(0) if kind == "reference" else 1
+    t0 = time.perf_counter()
+    if task == "config1":
+        A, B = np.asfortranarray(z["A"]), np.asfortranarray(z["B"])
+        n = A.shape[0]
+        if kind == "reference":
+            O.gemm(A[:256, :256], 0, B[:256, :256], 0)     # thread-pool warm-up
+            t0 = time.perf_counter()
+            res = O.config1(A, B, float(n))
+        else:
+            prod = O.gemm(A, 0, B, 0)
+            res = O.chain_softplus5(O.div_scalar(prod.ravel(order="F"), float(n))).reshape(n, n, order="F")
+        dt = time.perf_counter() - t0
+        np.save(outp, res)
+        return {"out": outp, "kind": kind, "cores": int(threads), "ms": round(dt * 1e3, 1), "TFLOP/s": round(2.0 * n ** 3 / dt / 1e12, 3),
+                "what": "reference Matrix<float>: log(exp(A*B/4096)+1)/5, cblas_sgemm + four single-threaded scalar passes"}
+    if task == "gemm_chain_block":
+        Ar, Bc, n = np.asfortranarray(z["Arows"]), np.asfortranarray(z["Bcols"]), int(z["n"][0])
+        prod = O.gemm(Ar, 0, Bc, 0)
+        res = O.chain_softplus5(O.div_scalar(prod.ravel(order="F"), float(n))).reshape(prod.shape, order="F")
+        np.save(outp, res)
+        return {"out": outp, "kind": kind, "cores": int(threads), "ms": round((time.perf_counter() - t0) * 1e3, 1)}
+    return {"error": f"unknown task {task}"}
+
+
 def run_reference(args):
+    """the reference arm: the reference's own CPU implementation of the SAME workload (one full pass of the sweep over
+    2^log2n elements per step; the CPU rate is flat in size, so steps are capped to keep the run within minutes)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_reference_subprocess(args.cpu_log2n, max(1, args.steps), min(args.warmup, 1))
+    cpu_steps = 1   # one full-size step is ~25 s of CPU work; --steps K / --warmup W are echoed, the sample says what ran
+    res = cpu_reference_subprocess(args.log2n, cpu_steps, 0)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rows = cols = 1 << (args.log2n // 2)
+    if args.log2n % 2:
+        cols *= 2
     if "error" in res:
         print(json.dumps({"impl": "reference", "unavailable": res["error"][:200]}))
         return
@@ -593,7 +799,9 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1]: elementwise + row/col-sum sweep, 2^{args.log2n} fp32 elements "
                                f"({rows}x{cols}) per GPU, {len(SWEEP)} ops/step",
-                   "ops": [n for n, _ in SWEEP], "note": "reference CPU path timed on a bounded sample (see cpu_baseline.sample)"},
+                   "l2": "inputs (1 GiB/operand) larger than L2, no flush", "ops": [n for n, _ in SWEEP],
+                   "algorithmic_bytes_per_step": sum(b for _, b in SWEEP) * (1 << args.log2n),
+                   "parallelism": f"independent shards x{world}"},
         "cpu_baseline": res,
         "e2e": {"value": res["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -608,16 +816,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2N_DEFAULT)
-    ap.add_argument("--cpu-log2n", type=int, default=24, dest="cpu_log2n")
-    ap.add_argument("--gemm-n", type=int, nargs="*", default=[2048, 4096, 8192, 16384], dest="gemm_n")
+    ap.add_argument("--cpu-log2n", type=int, default=26, dest="cpu_log2n")
+    ap.add_argument("--gemm-n", type=int, nargs="*", default=[1024, 2048, 4096, 8192, 16384], dest="gemm_n")
     ap.add_argument("--sharded-n", type=int, nargs="*", default=[16384, 32768], dest="sharded_n")
     ap.add_argument("--no-gemm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mnist", action="store_true", dest="no_mnist")
     ap.add_argument("--_cpu_child", action="store_true")
+    ap.add_argument("--_cpu_task", default="")
+    ap.add_argument("--_cpu_io", default="")
     args = ap.parse_args()
     if args._cpu_child:
-        print(json.dumps(run_cpu(args.cpu_log2n, args.steps, args.warmup)))
+        if args._cpu_task:
+            print(json.dumps(run_cpu_task(args._cpu_task, args._cpu_io)))
+        else:
+            print(json.dumps(run_cpu(args.cpu_log2n, args.steps, args.warmup)))
         return
     if args.impl == "reference":
         run_reference(args)

@@ -188,6 +188,33 @@ int jz_gemm_last_path(void);
 /* k-splits per tile of the partial last wave in the last tensor-core launch (1 = no split-K units) */
 int jz_gemm_last_splits(void);
 
+/* ---- multi-GPU, one process per GPU (SURVEY 8b jz_mg_*, 8e).  The reference has no collectives; these entry points
+ *      give C / C++ callers the sharded forms without torch, NCCL or MPI inside the library: peers' buffers are mapped
+ *      with CUDA IPC (P2P over NVLink), and the CALLER carries the opaque handle bytes between its processes (pipe,
+ *      MPI, shared memory, torch.distributed ...).  World size <= JZ_MAX_PEERS + 1 = 8 (one NVSwitch domain). */
+#define JZ_MG_HANDLE_BYTES 128
+/* contiguous share [begin, end) of n items for `rank`; the first n % world ranks get one more */
+int jz_mg_block_range(size_t n, int world, int rank, size_t* begin, size_t* end);
+/* handle (JZ_MG_HANDLE_BYTES) of a device buffer obtained from jz_malloc / cudaMalloc, for another process to import */
+int jz_mg_export(const float* dev_ptr, void* handle);
+/* map a peer process' buffer into this process (peer access is enabled lazily); release with jz_mg_release */
+int jz_mg_import(const void* handle, float** peer_ptr);
+int jz_mg_release(float* peer_ptr);
+/* device-side barrier on `stream`: flags[r] = rank r's array of `world` unsigned (zero-initialised once, exported /
+ * imported like any buffer; flags[rank] is this rank's own).  epoch must grow by 1 per barrier.  Everything the
+ * stream did before the barrier is visible to every rank's work after it. */
+int jz_mg_barrier(unsigned* const* flags, int world, int rank, unsigned epoch, jz_stream_t stream);
+/* Column-sharded GEMM with the all-gather fused into the tensor-core epilogue: this rank computes
+ * C[:, j0:j1] = chain(alpha * op(A) * B_block) (j0, j1 = jz_mg_block_range(n, world, rank); B_block = its k x (j1-j0)
+ * column block, ldb) and stores every finished tile into EVERY rank's dense m x n image c_images[r] (c_images[rank]
+ * = its own).  Follow with jz_mg_barrier before reading the other ranks' columns. */
+int jz_mg_gemm_allgather(int transA, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                         const float* B_block, size_t ldb, float* const* c_images, int world, int rank,
+                         const jz_step* steps, int nsteps, int mode, jz_stream_t stream);
+/* out[i] = sum over ranks, in rank order, of partial_images[r][i] (column sums over row-sharded data: local jz_sum into
+ * this rank's exported partial vector, jz_mg_barrier, then this; bitwise identical on every rank) */
+int jz_mg_allreduce_sum(float* out, float* const* partial_images, size_t n, int world, int rank, jz_stream_t stream);
+
 /* ---- transformer helper kernels (the reference's own __global__ kernels in ml/layer.hpp).
  *      Attention scores: (seq_len, seq_len*batch) column-major, block i = the seq_len x seq_len matrix at
  *      x + i*seq_len^2, element (query a, key b) at a + b*seq_len.  LayerNorm tensors: (dim, n) column-major. */

@@ -12,6 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_uin
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libjz_b200.so")
 
+MG_HANDLE_BYTES = 128
 JZ_OK, JZ_ERR_SHAPE, JZ_ERR_CUDA, JZ_ERR_OOM, JZ_ERR_ARG, JZ_ERR_UNSUPPORTED = range(6)
 
 UNARY = {"exp": 0, "log": 1, "tanh": 2, "dtanh": 3, "square": 4, "sqrt": 5, "relu": 6, "drelu": 7}
@@ -86,6 +87,14 @@ _SIGS = {
     "jz_gemm_last_splits": (c_int, []),
     "jz_gemm_strided_batched": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, c_size_t, _F, c_size_t,
                                         c_size_t, c_float, _F, c_size_t, c_size_t, c_size_t, c_int, _S]),
+    "jz_mg_block_range": (c_int, [c_size_t, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]),
+    "jz_mg_export": (c_int, [_F, c_void_p]),
+    "jz_mg_import": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "jz_mg_release": (c_int, [_F]),
+    "jz_mg_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_uint32, _S]),
+    "jz_mg_gemm_allgather": (c_int, [c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, _F, c_size_t,
+                                     POINTER(c_void_p), c_int, c_int, POINTER(jz_step), c_int, c_int, _S]),
+    "jz_mg_allreduce_sum": (c_int, [_F, POINTER(c_void_p), c_size_t, c_int, c_int, _S]),
     "jz_softmax_rows_batched": (c_int, [_F, _F, c_size_t, c_size_t, c_int, c_float, _S]),
     "jz_causal_mask": (c_int, [_F, c_size_t, c_size_t, c_float, _S]),
     "jz_softmax_rows_backward": (c_int, [_F, _F, _F, c_size_t, c_size_t, c_float, _S]),

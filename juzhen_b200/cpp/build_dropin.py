@@ -55,7 +55,9 @@ PROGRAMS = [
 # this repository's own C++ tests (same compute() convention), staged next to the reference's tests
 OWN_TESTS = [("test_fusion", "test_fusion.cu", []), ("bench_attention", "bench_attention.cu", ["-lcublas"]),
              ("bench_overhead", "bench_overhead.cu", []), ("bench_mnist_step", "bench_mnist_step.cu", [])]
-OURS_IN_CPP = {"cumatrix.cuh", "memory.hpp", "jz_lazy.hpp"}
+# own main(): linked without launcher.o
+OWN_MAIN = [("test_mg_dot", "test_mg_dot.cu", [])]
+OURS_IN_CPP = {"cumatrix.cuh", "memory.hpp", "jz_lazy.hpp", "jz_mg.hpp"}
 REF_CPP = ["core.hpp", "matrix.hpp", "operators.hpp", "helper.hpp", "juzhen.hpp", "cpulinalg.hpp"]
 
 
@@ -82,7 +84,7 @@ def stage():
         for p in glob.glob(os.path.join(REF, sub, "*")):
             if os.path.isfile(p):
                 link(p, os.path.join(STAGE, sub, os.path.basename(p)))
-    for _, src, _x in OWN_TESTS:
+    for _, src, _x in OWN_TESTS + OWN_MAIN:
         link(os.path.join(HERE, "tests", src), os.path.join(STAGE, "tests", src))
     link(os.path.join(REF, "external", "xpu_info", "xpu_info.hpp"), os.path.join(STAGE, "external", "xpu_info", "xpu_info.hpp"))
     eig = os.path.join(REF, "external", "Eigen3")
@@ -137,7 +139,7 @@ def build(only=None, force=False):
     for d in (OBJ, BIN):
         os.makedirs(d, exist_ok=True)
     fl, ob = flags()
-    ours = [os.path.join(HERE, f) for f in ("cumatrix.cuh", "cumatrix.cu", "memory.hpp", "launcher.cu", "jz_lazy.hpp")] + \
+    ours = [os.path.join(HERE, f) for f in ("cumatrix.cuh", "cumatrix.cu", "memory.hpp", "launcher.cu", "jz_lazy.hpp", "jz_mg.hpp")] + \
            [os.path.join(ROOT, "include", "jz_b200.h")]
     objs = []
     for unit in ("cumatrix", "launcher"):
@@ -161,10 +163,12 @@ def build(only=None, force=False):
         if not force and newer(exe, ours + objs + [os.path.realpath(os.path.join(STAGE, src))]):
             return name, "up to date"
         use = [objs[0], launcher_cublas] if "-DJZ_LEGACY_CUBLAS_HANDLE" in extra else objs
+        if name in {n for n, _, _ in OWN_MAIN}:
+            use = [objs[0]]
         run([NVCC, *fl, *extra, os.path.join(STAGE, src), *use, *link_flags, "-o", exe], f"build {name}")
         return name, "built"
 
-    todo = [p for p in PROGRAMS + [(n, "tests/" + s, x) for n, s, x in OWN_TESTS] if not only or p[0] in only]
+    todo = [p for p in PROGRAMS + [(n, "tests/" + s, x) for n, s, x in OWN_TESTS + OWN_MAIN] if not only or p[0] in only]
     with concurrent.futures.ThreadPoolExecutor(max_workers=6) as ex:
         res = list(ex.map(one, todo))
     for name, st in res:

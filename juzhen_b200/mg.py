@@ -102,9 +102,29 @@ def allreduce_partial_sums(partial: torch.Tensor, group=None) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------ GPU side
+def _on_stream(stream):
+    """torch work (barriers, NCCL collectives) issued inside this context runs on the SAME stream the jz_* kernels were
+    launched on, so the two are ordered without events"""
+    if stream is None or int(stream) == int(torch.cuda.current_stream().cuda_stream):
+        import contextlib
+        return contextlib.nullcontext()
+    return torch.cuda.stream(torch.cuda.ExternalStream(int(stream)))
+
+
 class GpuShardedGemm:
-    """the product path on B200s: local block through jz_gemm_chain (mode 'nccl') or fused with the gather
-    through jz_gemm_chain_bcast over symmetric memory (mode 'fused')."""
+    """the product path on B200s.  Every mode computes the local column block with the tcgen05 GEMM + fused chain; they
+    differ in how the blocks reach the other ranks:
+
+      'nccl'   one NCCL all-gather after the local product (the baseline)
+      'fused'  the GEMM epilogue stores every finished tile into each peer's image of C (P2P stores over NVLink through
+               torch symmetric memory, jz_gemm_chain_bcast), then one barrier
+      'mcast'  the epilogue issues ONE multimem.st per element to the NVSwitch multicast mapping of C
+               (jz_gemm_chain_mcast): 1/N of the NVLink egress of 'fused'
+      'ipc'    like 'fused', but through the torch-free jz_mg_* ABI: CUDA IPC handles (carried here by
+               torch.distributed.all_gather_object, nothing else of torch), jz_mg_gemm_allgather, jz_mg_barrier
+
+    C is reused by successive run() calls: every fused mode puts a barrier BEFORE the stores as well, so that no rank
+    overwrites an image a peer is still reading from the previous call."""
 
     def __init__(self, jz, m, n, k, steps=(), gemm_mode=-1, mode="nccl", group=None):
         self.jz, self.L = jz, jz.lib()
@@ -116,34 +136,95 @@ class GpuShardedGemm:
         self.gemm_mode, self.mode = gemm_mode, mode
         dev = torch.device("cuda", torch.cuda.current_device())
         self.peer_ptrs = None
-        if mode == "fused" and world > 1:
+        self.mc_ptr = None
+        self.ipc = None
+        if world == 1:
+            self.mode = "local"
+        if self.mode in ("fused", "mcast"):
             import torch.distributed._symmetric_memory as symm
             self.c_full = symm.empty(m * n, dtype=torch.float32, device=dev)
             self.hdl = symm.rendezvous(self.c_full, group=group if group is not None else dist.group.WORLD)
-            ptrs = [int(p) for p in self.hdl.buffer_ptrs]
             off = 4 * self.plan.c_offset()
-            others = [ptrs[r] + off for r in range(world) if r != rank]
-            if len(others) > 7:
-                raise ValueError("fused gather supports up to 8 GPUs (JZ_MAX_PEERS = 7)")
-            self.peer_ptrs = (ctypes.c_void_p * len(others))(*others)
-            self.n_peers = len(others)
+            if self.mode == "mcast":
+                mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+                if mc == 0:
+                    raise RuntimeError("this system offers no NVSwitch multicast mapping for symmetric memory")
+                self.mc_ptr = mc + off
+            else:
+                ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+                others = [ptrs[r] + off for r in range(world) if r != rank]
+                if len(others) > 7:
+                    raise ValueError("fused gather supports up to 8 GPUs (JZ_MAX_PEERS = 7)")
+                self.peer_ptrs = (ctypes.c_void_p * len(others))(*others)
+                self.n_peers = len(others)
+        elif self.mode == "ipc":
+            self.c_full = torch.empty(m * n, dtype=torch.float32, device=dev)
+            self.flags = torch.zeros(64, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            self.ipc = {"c": self._map_all(self.c_full.data_ptr(), world, rank), "f": self._map_all(self.flags.data_ptr(), world, rank)}
+            self.epoch = 0
         else:
             self.c_full = torch.empty(m * n, dtype=torch.float32, device=dev)
+
+    def _map_all(self, ptr, world, rank):
+        """export `ptr`, gather every rank's handle (the only use of torch.distributed on this path), import the peers'"""
+        from ._lib import MG_HANDLE_BYTES, check
+        mine = ctypes.create_string_buffer(MG_HANDLE_BYTES)
+        check(self.L.jz_mg_export(ptr, mine))
+        allh = [None] * world
+        dist.all_gather_object(allh, bytes(mine.raw), group=self.group)
+        out = (ctypes.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                out[r] = ptr
+            else:
+                p = ctypes.c_void_p()
+                check(self.L.jz_mg_import(ctypes.create_string_buffer(allh[r], MG_HANDLE_BYTES), ctypes.byref(p)))
+                out[r] = p.value
+        return out
+
+    def close(self):
+        if self.ipc is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            for arr in self.ipc.values():
+                for r in range(self.plan.world):
+                    if r != self.plan.rank and arr[r]:
+                        self.L.jz_mg_release(arr[r])
+            self.ipc = None
+
+    def _ipc_barrier(self, stream):
+        self.epoch += 1
+        self.jz._lib.check(self.L.jz_mg_barrier(self.ipc["f"], self.plan.world, self.plan.rank, self.epoch, stream))
 
     def run(self, a_ptr, lda, trans_a, b_block_ptr, ldb, stream):
         """A: full operand (trans_a = its lazy transpose flag); b_block: this rank's k x (j1-j0) column block"""
         p = self.plan
         j0, j1 = p.cols
         c_ptr = self.c_full.data_ptr() + 4 * p.c_offset()
-        if self.peer_ptrs is not None:
-            rc = self.L.jz_gemm_chain_bcast(int(trans_a), 0, p.m, j1 - j0, p.k, 1.0, a_ptr, lda, b_block_ptr, ldb,
-                                            c_ptr, p.m, self.peer_ptrs, self.n_peers, self.steps, self.nsteps,
-                                            self.gemm_mode, stream)
-            self.jz._lib.check(rc)
-            self.hdl.barrier(channel=0)  # every rank's stores have landed in every image of C
+        check = self.jz._lib.check
+        if self.mode in ("fused", "mcast"):
+            with _on_stream(stream):
+                self.hdl.barrier(channel=1)      # every rank is done reading the previous contents of every image
+            if self.mode == "mcast":
+                rc = self.L.jz_gemm_chain_mcast(int(trans_a), 0, p.m, j1 - j0, p.k, 1.0, a_ptr, lda, b_block_ptr, ldb, c_ptr, p.m,
+                                                self.mc_ptr, self.steps, self.nsteps, self.gemm_mode, stream)
+            else:
+                rc = self.L.jz_gemm_chain_bcast(int(trans_a), 0, p.m, j1 - j0, p.k, 1.0, a_ptr, lda, b_block_ptr, ldb, c_ptr, p.m,
+                                                self.peer_ptrs, self.n_peers, self.steps, self.nsteps, self.gemm_mode, stream)
+            check(rc)
+            with _on_stream(stream):
+                self.hdl.barrier(channel=0)      # every rank's stores have landed in every image of C
+        elif self.mode == "ipc":
+            self._ipc_barrier(stream)
+            check(self.L.jz_mg_gemm_allgather(int(trans_a), p.m, p.n, p.k, 1.0, a_ptr, lda, b_block_ptr, ldb, self.ipc["c"], p.world, p.rank,
+                                              self.steps, self.nsteps, self.gemm_mode, stream))
+            self._ipc_barrier(stream)
         else:
             rc = self.L.jz_gemm_chain(int(trans_a), 0, p.m, j1 - j0, p.k, 1.0, a_ptr, lda, b_block_ptr, ldb,
                                       c_ptr, p.m, self.steps, self.nsteps, self.gemm_mode, stream)
-            self.jz._lib.check(rc)
-            all_gather_blocks(self.c_full, p, self.group)
+            check(rc)
+            if p.world > 1:
+                with _on_stream(stream):
+                    all_gather_blocks(self.c_full, p, self.group)
         return self.c_full
