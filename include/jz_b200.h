@@ -160,6 +160,14 @@ int jz_gemm(int transA, int transB, size_t m, size_t n, size_t k, float alpha,
 int jz_gemm_chain(int transA, int transB, size_t m, size_t n, size_t k, float alpha,
                   const float* A, size_t lda, const float* B, size_t ldb,
                   float* C, size_t ldc, const jz_step* steps, int nsteps, int mode, jz_stream_t stream);
+/* same, with a broadcast stage in front of the steps: C = chain(s1*(alpha*A*B) + s2*bias[i]) (bias_dim 1: one value
+ * per row, length m) or + s2*bias[j] (bias_dim 0: per column, length n).  This is W*x + b*ones(1,N) followed by the
+ * activation (Layer::eval / Layer::grad, ml/layer.hpp:79,120) as ONE kernel; bit-identical to jz_gemm + jz_add_bcast +
+ * jz_chain.  bias == NULL: no broadcast stage. */
+int jz_gemm_bias_chain(int transA, int transB, size_t m, size_t n, size_t k, float alpha,
+                       const float* A, size_t lda, const float* B, size_t ldb,
+                       float* C, size_t ldc, const float* bias, int bias_dim, float s1, float s2,
+                       const jz_step* steps, int nsteps, int mode, jz_stream_t stream);
 /* Multi-GPU form (column-sharded C = A * B[:, block], then all-gather): the same fused product,
  * whose epilogue ALSO stores every finished tile into `n_peers` more images of C with the same ldc --
  * buffers of peer GPUs mapped into this process (CUDA P2P / symmetric memory over NVLink).  The gather

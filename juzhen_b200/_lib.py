@@ -80,6 +80,8 @@ _SIGS = {
                         c_float, _F, c_size_t, c_int, _S]),
     "jz_gemm_chain": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, _F, c_size_t,
                               _F, c_size_t, POINTER(jz_step), c_int, c_int, _S]),
+    "jz_gemm_bias_chain": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, _F, c_size_t,
+                                   _F, c_size_t, _F, c_int, c_float, c_float, POINTER(jz_step), c_int, c_int, _S]),
     "jz_gemm_chain_bcast": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, _F, c_size_t,
                                     _F, c_size_t, POINTER(c_void_p), c_int, POINTER(jz_step), c_int, c_int, _S]),
     "jz_gemm_chain_mcast": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, _F, c_size_t,

@@ -87,8 +87,14 @@ static void run_gemm(Producer& g, float* out, const std::vector<jz_step>& epilog
     g.a->materialize();
     g.b->materialize();
     const size_t fused = std::min(epilogue.size(), size_t(JZ_MAX_CHAIN));
-    JZ_DO(jz_gemm_chain(g.ta, g.tb, g.m, g.n, g.k, 1.0f, g.a->ptr, g.lda, g.b->ptr, g.ldb, out, g.m ? g.m : 1,
-                        epilogue.data(), int(fused), -1, S()));
+    if (g.bias) {   // product + broadcast add + elementwise program: one kernel
+        g.bias->materialize();
+        JZ_DO(jz_gemm_bias_chain(g.ta, g.tb, g.m, g.n, g.k, 1.0f, g.a->ptr, g.lda, g.b->ptr, g.ldb, out, g.m ? g.m : 1, g.bias->ptr,
+                                 g.bias_dim, g.bias_s1, g.bias_s2, epilogue.data(), int(fused), -1, S()));
+    } else {
+        JZ_DO(jz_gemm_chain(g.ta, g.tb, g.m, g.n, g.k, 1.0f, g.a->ptr, g.lda, g.b->ptr, g.ldb, out, g.m ? g.m : 1,
+                            epilogue.data(), int(fused), -1, S()));
+    }
     if (fused < epilogue.size())
         run_program(out, out, g.m * g.n, std::vector<jz_step>(epilogue.begin() + fused, epilogue.end()));
 }
@@ -407,6 +413,21 @@ bool Matrix<CUDAfloat>::add_broadcast(const Matrix<CUDAfloat>& B, float s1, floa
     // this = s1*this + s2*(u 1^T): one pass over this
     if (const Producer* g = theirs->producer.get(); g && g->a != mine && g->b != mine) {
         if (StoragePtr vec = deferred_broadcast(*theirs, numrow, numcol, dim)) {
+            // `this` is itself a product that has not run yet (W*x + b*ones(1,N)): the broadcast becomes a stage of
+            // its epilogue, and whatever elementwise steps follow (tanh, d_tanh) join it there -- one kernel in all
+            if (mine->lazy_ok() && vec != mine) {
+                mine->flush_readers();   // deferred readers were defined on the product without the broadcast
+                Producer* mg = mine->producer.get();
+                if (mg && mg->kind == Producer::GEMM && mg->k > 1 && !mg->bias && mine->pending.empty() && mg->a != vec && mg->b != vec) {
+                    mg->bias = vec;
+                    mg->bias_dim = dim;
+                    mg->bias_s1 = s1;
+                    mg->bias_s2 = s2;
+                    jzb200::add_reader(vec, mine);   // if the vector changes first, the product runs with today's values
+                    if (theirs->producer) theirs->producer->consumed = true;
+                    return true;
+                }
+            }
             vec->materialize();
             float* x = wdev();
             JZ_DO(jz_add_bcast(x, x, numrow, numcol, vec->ptr, dim, s1, s2, S()));

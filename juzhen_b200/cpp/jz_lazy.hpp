@@ -41,6 +41,11 @@ struct Producer {
     int ta = 0, tb = 0;
     size_t m = 0, n = 0, k = 0, lda = 0, ldb = 0;
     bool consumed = false;   // its value already went into a fused pass (broadcast add): need not run if it dies unread
+    // optional broadcast stage of the GEMM epilogue: C = bias_s1*(A*B) + bias_s2*bias[i] (dim 1) / bias[j] (dim 0), the
+    // W*x + b*ones(1,N) idiom (ml/layer.hpp:79,120) folded into the product that has not run yet
+    StoragePtr bias;
+    int bias_dim = 0;
+    float bias_s1 = 1.0f, bias_s2 = 0.0f;
     // MAP: out[i] = steps(src[i]) over the flat physical buffer
     StoragePtr src;
     std::vector<jz_step> steps;

@@ -267,6 +267,28 @@ int compute() {
         check(rel_fro(keep(out.to_host()), A * B) < 1e-5f, "and the last one is the product");
     }
 
+    // (14b) Layer::eval / Layer::grad (ml/layer.hpp:79,120): tanh(W*x + b*ones(1,N)) is ONE kernel -- product, broadcast
+    //       stage and activation in the GEMM epilogue -- for a latency-bound (small-product kernel) and a tensor-core shape
+    for (size_t N : {size_t(40), size_t(512)}) {
+        const size_t m = N == 40 ? 96 : 384, k = N == 40 ? 200 : 320;
+        auto W = Matrix<float>::randn(m, k) * 0.1, x = Matrix<float>::randn(k, N), b = Matrix<float>::randn(m, 1);
+        CM dW(W), dx(x), db(b);
+        jz_sync(nullptr);
+        const unsigned long long before = jz_launch_count();
+        CM R = tanh(dW * dx + db * CM::ones(1, N));
+        Matrix<float> got = keep(R.to_host());
+        const unsigned long long launches = jz_launch_count() - before;
+        Matrix<float> want = tanh(W * x + b * Matrix<float>::ones(1, N));
+        std::cout << "    tanh(W*x + b*ones) N=" << N << ": launches " << launches << ", rel_fro vs CPU " << rel_fro(got, want) << std::endl;
+        check(rel_fro(got, want) < 1e-5f, "tanh(W*x + b*ones(1,N)) matches the CPU path");
+        const char* eager = std::getenv("JZ_EAGER");
+        if (!(eager && *eager && std::string(eager) != "0")) check(launches == 1, "fused: one GEMM launch with bias + activation epilogue");
+        CM G = d_tanh(dW * dx + db * CM::ones(1, N));
+        db += db;   // the deferred product must run with the bias it was defined on
+        Matrix<float> got2 = keep(G.to_host());
+        check(rel_fro(got2, d_tanh(W * x + b * Matrix<float>::ones(1, N))) < 1e-5f, "a bias modified after the deferral does not leak into it");
+    }
+
     // (15) random programs over a pool of matrices: every aliasing pattern the API allows (source == destination, T()
     //      views of the destination, copies taken before a source changes, rvalue chains, products feeding chains,
     //      broadcast idioms, refills).  The dump of this section must be bit-identical between the deferred and the
@@ -278,7 +300,7 @@ int compute() {
         for (int i = 0; i < 6; i++) pool.emplace_back(CM(Matrix<float>::randn(d, d)));
         bool finite = true;
         for (int step = 0; step < 400; step++) {
-            const int op = rng() % 14, i = rng() % 6, j = rng() % 6, k = rng() % 6;
+            const int op = rng() % 17, i = rng() % 6, j = rng() % 6, k = rng() % 6;
             switch (op) {
                 case 0: pool[k] = tanh(pool[i]); break;
                 case 1: pool[k] = tanh(std::move(pool[k]) * 0.5f + 0.1f); break;
@@ -293,6 +315,10 @@ int compute() {
                 case 10: pool[k].zeros(); pool[k] += pool[i]; break;
                 case 11: pool[k] = tanh(CM::ones(d, d) * 0.25f + pool[i] * pool[j].T() / (float)d); break;
                 case 12: { CM t = pool[i]; pool[i] = tanh(std::move(pool[i]) * 1.5f); pool[k] = t - pool[i]; pool[k] = tanh(std::move(pool[k])); break; }
+                case 13: pool[k] = tanh(pool[i] * pool[j] + sum(pool[j], 1) * CM::ones(1, d)); break;          // W*x + b*ones(1,N)
+                case 14: { CM bcol = sum(pool[i], 1) / (float)d; CM g = d_tanh(pool[i].T() * pool[j] + bcol * CM::ones(1, d));
+                           bcol += bcol; pool[k] = hadmd(g, pool[j]); break; }                                  // bias changes after the deferral
+                case 15: pool[k] = tanh(pool[i] * pool[j] - CM::ones(d, 1) * sum(pool[i], 0)); break;          // per-column broadcast
                 default: pool[k] = tanh(pool[i] - CM::ones(d, 1) * sum(pool[i], 0) / (float)d); break;
             }
             if (step % 20 == 19) {

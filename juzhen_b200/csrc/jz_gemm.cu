@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) sgemm_simt_kernel(size_t m, size_t n, siz
             const size_t gi = i0 + tx * 4 + r;
             float x = alpha * acc[r][c];
             if (beta != 0.0f && gi < m) x += beta * C[gj * ldc + gi];
+            if (chain.bias) x = apply_bias(x, chain, gi < m ? gi : 0, gj);
             v[r] = x;
         }
         if (chain.n) apply_chain<4>(v, chain);
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(256) rank1_kernel(size_t m, size_t n, float al
         for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < m; i += size_t(gridDim.x) * 256) {
             float x[1] = {u ? u[i * su] * vj : 0.0f};
             if (beta != 0.0f) x[0] += beta * C[j * ldc + i];
+            if (chain.bias) x[0] = apply_bias(x[0], chain, i, j);
             if (chain.n) apply_chain<1>(x, chain);
             C[j * ldc + i] = x[0];
         }
@@ -450,7 +452,7 @@ int jz_gemm(int transA, int transB, size_t m, size_t n, size_t k, float alpha, c
             const float* B, size_t ldb, float beta, float* C, size_t ldc, int mode, jz_stream_t stream) {
     JZ_INIT_OR_RETURN();
     ChainParams chain;
-    chain.n = 0;
+    make_chain(chain, nullptr, 0);
     return gemm_entry(transA, transB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, chain, mode, as_stream(stream));
 }
 
@@ -472,11 +474,14 @@ int jz_gemm_strided_batched(int transA, int transB, size_t m, size_t n, size_t k
     if (mode < 0) mode = ctx().gemm_mode;
     if (mode > JZ_GEMM_FP32_SIMT) return fail(JZ_ERR_ARG, "jz_gemm_strided_batched: bad mode %d", mode);
     ChainParams chain;
-    chain.n = 0;
+    make_chain(chain, nullptr, 0);
     cudaStream_t s = as_stream(stream);
     const double macs = double(m) * double(n) * double(k);
     static const bool no_btc = std::getenv("JZ_GEMM_NO_BATCHED_TC") != nullptr;
-    const bool tc_member = m >= 64 && n >= 64 && k >= 32 && macs * double(batch) >= double(1 << 22) && batch > 1 &&
+    // members of at least 2^21 multiply-adds (128 x 128 x 128): below that a tile's fixed cost (prologue, TMEM allocation,
+    // epilogue) exceeds its mainloop and the small-product kernel wins (measured: seq 64, d_h 128 at 0.7x cuBLAS fp32 on
+    // the tensor path, profiles/r02_attention.log)
+    const bool tc_member = m >= 64 && n >= 64 && k >= 32 && macs >= double(1 << 21) && batch > 1 &&
                            batch < (size_t(1) << 31) && (mode == JZ_GEMM_3XTF32 || mode == JZ_GEMM_TF32) && ctx().cc_major == 10 &&
                            m < (size_t(1) << 31) && n < (size_t(1) << 31) && k < (size_t(1) << 31) && !no_btc;
     const bool tma_ok = lda % 4 == 0 && ldb % 4 == 0 && strideA % 4 == 0 && strideB % 4 == 0 && aligned16(A) && aligned16(B);
@@ -506,6 +511,22 @@ int jz_gemm_chain(int transA, int transB, size_t m, size_t n, size_t k, float al
     JZ_INIT_OR_RETURN();
     ChainParams chain;
     if (make_chain(chain, steps, nsteps) != JZ_OK) return fail(JZ_ERR_ARG, "jz_gemm_chain: bad step list");
+    return gemm_entry(transA, transB, m, n, k, alpha, A, lda, B, ldb, 0.0f, C, ldc, chain, mode, as_stream(stream));
+}
+
+int jz_gemm_bias_chain(int transA, int transB, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
+                       const float* B, size_t ldb, float* C, size_t ldc, const float* bias, int bias_dim, float s1, float s2,
+                       const jz_step* steps, int nsteps, int mode, jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    ChainParams chain;
+    if (make_chain(chain, steps, nsteps) != JZ_OK) return fail(JZ_ERR_ARG, "jz_gemm_bias_chain: bad step list");
+    if (bias) {
+        if (bias_dim != 0 && bias_dim != 1) return fail(JZ_ERR_ARG, "jz_gemm_bias_chain: bias_dim must be 0 or 1");
+        chain.bias = bias;
+        chain.bias_dim = bias_dim;
+        chain.bias_s1 = s1;
+        chain.bias_s2 = s2;
+    }
     return gemm_entry(transA, transB, m, n, k, alpha, A, lda, B, ldb, 0.0f, C, ldc, chain, mode, as_stream(stream));
 }
 

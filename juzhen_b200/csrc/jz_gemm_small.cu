@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
                 float x[1] = {alpha * s};
                 float* dst = C + (j0 + j) * ldc + i;
                 if (beta != 0.0f) x[0] += beta * *dst;
+                if (chain.bias) x[0] = apply_bias(x[0], chain, i, j0 + j);
                 if (chain.n) apply_chain<1>(x, chain);
                 *dst = x[0];
             }
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
                     float x[1] = {alpha * acc[j]};
                     float* dst = C + (j0 + j) * ldc + i;
                     if (beta != 0.0f) x[0] += beta * *dst;
+                    if (chain.bias) x[0] = apply_bias(x[0], chain, i, j0 + j);
                     if (chain.n) apply_chain<1>(x, chain);
                     *dst = x[0];
                 }

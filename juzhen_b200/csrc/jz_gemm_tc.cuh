@@ -528,6 +528,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             src += ldc;
                         }
                     }
+                    if (s_chain.bias) {   // x = s1*x + s2*bias[row | column]: W*x + b*ones(1,N) as part of the product
+                        const float br = s_chain.bias_dim == 1 ? s_chain.bias[row_ok ? row : 0] : 0.0f;
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            const float bv = s_chain.bias_dim == 1 ? br : s_chain.bias[c < ncols ? colp + c : colp];
+                            v[c] = __fadd_rn(__fmul_rn(s_chain.bias_s1, v[c]), __fmul_rn(s_chain.bias_s2, bv));
+                        }
+                    }
                     if (s_chain.n) apply_chain<32>(v, s_chain);
                     // a warp writes 32 consecutive floats (128 B) per column.  Multi-GPU (fused all-gather): either ONE
                     // multimem.st per element to the multicast image (NVSwitch replicates it into every GPU's C,
@@ -615,6 +623,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int q = 0; q < 4; q++)
                             if (row0 + q < args.m) v[q] += args.beta * dstc[q];
+                    }
+                    if (s_chain.bias) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) v[q] = apply_bias(v[q], s_chain, row0 + q < args.m ? row0 + q : row0, col);
                     }
                     if (s_chain.n) apply_chain<4>(v, s_chain);
                     if (args.mc) {

@@ -163,7 +163,16 @@ struct ChainParams {
     int kind[JZ_MAX_CHAIN];
     float s1[JZ_MAX_CHAIN];
     float a[JZ_MAX_CHAIN];
+    // GEMM epilogues only: a broadcast stage applied BEFORE the steps, x = bias_s1*x + bias_s2*bias[dim == 1 ? row : col]
+    // (W*x + b*ones(1,N), ml/layer.hpp:79,120), rounded exactly like the separate jz_add_bcast pass
+    const float* bias;
+    int bias_dim;
+    float bias_s1, bias_s2;
 };
+
+__device__ __forceinline__ float apply_bias(float x, const ChainParams& c, size_t row, size_t col) {
+    return __fadd_rn(__fmul_rn(c.bias_s1, x), __fmul_rn(c.bias_s2, c.bias[c.bias_dim == 1 ? row : col]));
+}
 
 // Applies the steps in order to a register tile.  `c` must live in SHARED memory (stage it with
 // stage_chain): indexing a kernel-parameter struct with the runtime step counter makes nvcc emit a
@@ -176,15 +185,20 @@ __device__ __forceinline__ void apply_chain(float (&v)[N], const ChainParams& c)
     for (int s = 0; s < n; s++) apply_step<N>(v, c.kind[s], c.s1[s], c.a[s]);
 }
 
-// cooperative copy of the kernel-parameter chain into shared memory (call before __syncthreads)
+// copy of the kernel-parameter chain into shared memory (call before __syncthreads).  ONE thread copies the struct
+// with static offsets (constant-bank loads): indexing the parameter with the thread id instead makes nvcc spill a
+// private copy of the whole struct to every thread's local memory first (128 bytes of stack, measured as a drop of
+// the fused chain from 0.86 to 0.68 of the HBM peak when the struct grew past 25 words).
 __device__ __forceinline__ void stage_chain(ChainParams* dst, const ChainParams& src, int tid) {
-    constexpr int kWords = int(sizeof(ChainParams) / sizeof(int));
-    if (tid < kWords) reinterpret_cast<int*>(dst)[tid] = reinterpret_cast<const int*>(&src)[tid];
+    if (tid == 0) *dst = src;
 }
 
 inline int make_chain(ChainParams& c, const jz_step* steps, int nsteps) {
     if (nsteps < 0 || nsteps > JZ_MAX_CHAIN || (nsteps > 0 && !steps)) return JZ_ERR_ARG;
     c.n = nsteps;
+    c.bias = nullptr;
+    c.bias_dim = 0;
+    c.bias_s1 = c.bias_s2 = 0.0f;
     for (int i = 0; i < nsteps; i++) {
         const int k = steps[i].kind;
         if (!((k >= 0 && k < JZ_UNARY_COUNT) || k == JZ_STEP_AFFINE || k == JZ_STEP_ELEMINV)) return JZ_ERR_ARG;

@@ -349,32 +349,56 @@ __global__ void __launch_bounds__(256) softmax_warp_kernel(float* out, const flo
     }
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, L2 only) and the wait for this thread's own copies
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
 // ---- register-cached column softmax: the column is read ONCE (128-bit loads), kept in registers
 // through max / exp / sum / scale, and written ONCE: 8 B/elem of HBM traffic, the algorithmic
 // minimum.  G threads cooperate on one column: a warp (G = 32, 8 columns per CTA) for rows up to
 // 2048, a whole 512-thread CTA (G = 512) for rows up to 32768.  mode 1 fuses the softmax-CE
 // gradient -(y - s)/nb (ml/layer.hpp:263) into the same pass.
-template <int NV, bool BLOCK>
+// PREF (long columns, one CTA per SM): the phases of a column serialise inside the CTA (load everything, reduce,
+// exponentiate, reduce, store), so HBM idles while the CTA computes.  With PREF every thread copies ITS elements of
+// the NEXT column into a private slice of shared memory with cp.async while it works on the current one from
+// registers, and starts the next column from shared memory: loads of column c+1 overlap the math and the stores of
+// column c (no extra barrier: a thread only ever reads back what it copied itself).
+template <int NV, bool BLOCK, bool PREF = false>
 __global__ void __launch_bounds__(BLOCK ? 512 : 256)
 softmax_reg_kernel(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode, float rnb) {
     constexpr int G = BLOCK ? 512 : 32;
+    static_assert(!PREF || BLOCK, "prefetch staging is for the CTA-per-column form");
+    extern __shared__ float4 sm_stage[];   // PREF: [NV][512]
     __shared__ float red[16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = BLOCK ? threadIdx.x : lane;
     const size_t n4 = rows >> 2;
     const size_t col_step = BLOCK ? gridDim.x : size_t(gridDim.x) * 8;
+    auto prefetch = [&](size_t c) {
+        const float4* col = reinterpret_cast<const float4*>(a + c * ld);
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const size_t i = size_t(g) + size_t(q) * G;
+            if (i < n4) cp_async16(&sm_stage[q * G + g], col + i);
+        }
+    };
+    if (PREF && blockIdx.x < cols) prefetch(blockIdx.x);
     for (size_t c = BLOCK ? blockIdx.x : size_t(blockIdx.x) * 8 + warp; c < cols; c += col_step) {
         const float4* col = reinterpret_cast<const float4*>(a + c * ld);
         float4 v[NV];
         float m = -1e30f;
+        if (PREF) cp_async_wait_all();
 #pragma unroll
         for (int q = 0; q < NV; q++) {
             const size_t i = size_t(g) + size_t(q) * G;
             if (i < n4) {
-                v[q] = col[i];
+                v[q] = PREF ? sm_stage[q * G + g] : col[i];
                 m = fmaxf(m, fmaxf(fmaxf(v[q].x, v[q].y), fmaxf(v[q].z, v[q].w)));
             }
         }
+        if (PREF && c + col_step < cols) prefetch(c + col_step);
         m = warp_reduce<MaxOp>(m);
         if (BLOCK) {
             __syncthreads();  // protects `red` from the previous column's readers
@@ -661,18 +685,31 @@ softmax_cluster_kernel(float* out, const float* a, const float* y, size_t rows, 
     const size_t seg = (n4 + CL - 1) / CL;                  // float4 words per CTA
     const size_t lo = size_t(r) * seg, hi = lo + seg < n4 ? lo + seg : n4;
     const size_t ncl = gridDim.x / CL;
-    for (size_t c = blockIdx.x / CL; c < cols; c += ncl) {
+    // the next column's share is copied into shared memory (cp.async, per-thread private slots) while this one is
+    // reduced, exponentiated and stored: see softmax_reg_kernel's PREF
+    extern __shared__ float4 sm_stage[];   // [NV][512]
+    auto prefetch = [&](size_t c) {
         const float4* col = reinterpret_cast<const float4*>(a + c * ld);
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const size_t i = lo + threadIdx.x + size_t(q) * 512;
+            if (i < hi) cp_async16(&sm_stage[q * 512 + threadIdx.x], col + i);
+        }
+    };
+    if (blockIdx.x / CL < cols) prefetch(blockIdx.x / CL);
+    for (size_t c = blockIdx.x / CL; c < cols; c += ncl) {
         float4 v[NV];
         float m = -1e30f;
+        cp_async_wait_all();
 #pragma unroll
         for (int q = 0; q < NV; q++) {
             const size_t i = lo + threadIdx.x + size_t(q) * 512;
             if (i < hi) {
-                v[q] = col[i];
+                v[q] = sm_stage[q * 512 + threadIdx.x];
                 m = fmaxf(m, fmaxf(fmaxf(v[q].x, v[q].y), fmaxf(v[q].z, v[q].w)));
             }
         }
+        if (c + ncl < cols) prefetch(c + ncl);
         m = warp_reduce<MaxOp>(m);
         if (lane == 0) red[warp] = m;
         __syncthreads();
@@ -730,12 +767,19 @@ softmax_cluster_kernel(float* out, const float* a, const float* y, size_t rows, 
 template <int NV, int CL>
 static int launch_softmax_cluster(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode,
                                   float rnb, cudaStream_t s) {
-    const size_t slots = size_t(ctx().sm_count) * 2 / CL;   // ~2 CTAs per SM
+    constexpr int SMEM = NV * 512 * 16;                       // the prefetch staging: 64 KB (NV = 8) or 128 KB (NV = 16)
+    static bool attr_done = false;
+    if (!attr_done) {
+        JZ_CUDA(cudaFuncSetAttribute(softmax_cluster_kernel<NV, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_done = true;
+    }
+    const size_t slots = size_t(ctx().sm_count) * (NV <= 8 ? 2 : 1) / CL;   // resident CTAs per SM by shared memory
     const size_t ncl = cols < slots ? cols : slots;
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(unsigned(ncl * CL), 1, 1);
     cfg.blockDim = dim3(512, 1, 1);
+    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -806,10 +850,25 @@ static int softmax_impl(float* out, const float* a, const float* y, size_t rows,
         } else {          // one 512-thread CTA per column
             const unsigned grid = unsigned(cols < cap * 4 ? cols : cap * 4);
 #define JZ_SM_BLOCK(NV) JZ_LAUNCH((softmax_reg_kernel<NV, true>), grid, 512, 0, s, out, a, y, rows, cols, ld, mode, rnb)
+            static const bool no_pref = std::getenv("JZ_SOFTMAX_NO_PREFETCH") != nullptr;
             if (n4 <= 1024) JZ_SM_BLOCK(2);
             else if (n4 <= 2048) JZ_SM_BLOCK(4);
-            else if (n4 <= 4096) JZ_SM_BLOCK(8);
-            else JZ_SM_BLOCK(16);
+            else if (n4 <= 4096 && (no_pref || cols < 2 * size_t(ctx().sm_count))) JZ_SM_BLOCK(8);
+            else if (no_pref || cols < 2 * size_t(ctx().sm_count)) JZ_SM_BLOCK(16);
+            else {
+                // long columns, several per SM: persistent CTAs (as many as stay resident) that prefetch their next column
+                static bool attr_done = false;
+                if (!attr_done) {
+                    JZ_CUDA(cudaFuncSetAttribute(softmax_reg_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 512 * 16));
+                    JZ_CUDA(cudaFuncSetAttribute(softmax_reg_kernel<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 512 * 16));
+                    attr_done = true;
+                }
+                const bool nv8 = n4 <= 4096;
+                const size_t resident = size_t(ctx().sm_count) * (nv8 ? 2 : 1);
+                const unsigned pgrid = unsigned(cols < resident ? cols : resident);
+                if (nv8) JZ_LAUNCH((softmax_reg_kernel<8, true, true>), pgrid, 512, 8 * 512 * 16, s, out, a, y, rows, cols, ld, mode, rnb);
+                else JZ_LAUNCH((softmax_reg_kernel<16, true, true>), pgrid, 512, 16 * 512 * 16, s, out, a, y, rows, cols, ld, mode, rnb);
+            }
 #undef JZ_SM_BLOCK
         }
         return JZ_OK;

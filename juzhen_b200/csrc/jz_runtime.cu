@@ -47,10 +47,18 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 static std::mutex g_init_mu;
+static int pool_prepare_device_switch();
+static void pool_mark_alive();
 
 static int do_init(int device) {
     std::lock_guard<std::mutex> lk(g_init_mu);
     if (g_ctx.inited && (device < 0 || device == g_ctx.device)) return JZ_OK;
+    if (g_ctx.inited) {
+        // the pool and the ticket blocks belong to the device they were allocated on (one process per GPU is the
+        // model): switching is allowed only when nothing is live, and the cached blocks go back to the old device
+        int rc = pool_prepare_device_switch();
+        if (rc != JZ_OK) return rc;
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -80,12 +88,22 @@ static int do_init(int device) {
         else if (!std::strcmp(gm, "tf32")) g_ctx.gemm_mode = JZ_GEMM_TF32;
         else if (!std::strcmp(gm, "fp32")) g_ctx.gemm_mode = JZ_GEMM_FP32_SIMT;
     }
+    pool_mark_alive();
     g_ctx.inited = true;
     return JZ_OK;
 }
 
 int ensure_init() {
-    if (g_ctx.inited) return JZ_OK;
+    if (g_ctx.inited) {
+        // a host thread other than the one that called jz_init starts on device 0: bind it once
+        static thread_local bool bound = false;
+        if (!bound) {
+            int cur = -1;
+            if (cudaGetDevice(&cur) != cudaSuccess || cur != g_ctx.device) JZ_CUDA(cudaSetDevice(g_ctx.device));
+            bound = true;
+        }
+        return JZ_OK;
+    }
     return do_init(-1);
 }
 
@@ -94,6 +112,7 @@ struct Block {
     void* ptr;
     size_t bytes;
     cudaStream_t freed_on;
+    cudaEvent_t freed_ev;   // recorded on freed_on when the block was released (nullptr: could not be recorded)
 };
 
 struct Pool {
@@ -111,7 +130,10 @@ struct Pool {
 
     int trim_locked() {
         for (auto& kv : cached)
-            for (auto& b : kv.second) cudaFree(b.ptr);
+            for (auto& b : kv.second) {
+                cudaFree(b.ptr);
+                if (b.freed_ev) events.push_back(b.freed_ev);
+            }
         cached.clear();
         cached_bytes = 0;
         return JZ_OK;
@@ -128,15 +150,17 @@ struct Pool {
             for (size_t i = vec.size(); i-- > 0;)
                 if (vec[i].freed_on == s) { pick = i; break; }
             Block b = vec[pick];
-            vec.erase(vec.begin() + pick);
             if (b.freed_on != s) {
-                cudaEvent_t ev;
-                if (!events.empty()) { ev = events.back(); events.pop_back(); }
-                else JZ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                JZ_CUDA(cudaEventRecord(ev, b.freed_on));
-                JZ_CUDA(cudaStreamWaitEvent(s, ev, 0));
-                events.push_back(ev);
+                // another stream: wait for the work that was queued on the freeing stream WHEN the block was released
+                // (the event was recorded then, so later work on that stream is not waited for and the stream need
+                // not exist any more).  On failure the block stays cached and the caller gets a fresh allocation.
+                if (!b.freed_ev || cudaStreamWaitEvent(s, b.freed_ev, 0) != cudaSuccess) {
+                    cudaGetLastError();
+                    goto fresh;
+                }
             }
+            vec.erase(vec.begin() + pick);
+            if (b.freed_ev) events.push_back(b.freed_ev);
             cached_bytes -= rb;
             live_bytes += rb;
             live.emplace(b.ptr, rb);
@@ -144,6 +168,7 @@ struct Pool {
             *out = b.ptr;
             return JZ_OK;
         }
+    fresh:
         void* p = nullptr;
         cudaError_t e = cudaMalloc(&p, rb);
         if (e != cudaSuccess) {
@@ -176,7 +201,16 @@ struct Pool {
         live.erase(it);
         live_bytes -= rb;
         cached_bytes += rb;
-        cached[rb].push_back(Block{p, rb, s});
+        // the point in the freeing stream after which the block may be reused from ANOTHER stream
+        cudaEvent_t ev = nullptr;
+        if (!events.empty()) { ev = events.back(); events.pop_back(); }
+        else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
+        if (ev && cudaEventRecord(ev, s) != cudaSuccess) {   // e.g. a capturing stream: same-stream reuse only
+            cudaGetLastError();
+            events.push_back(ev);
+            ev = nullptr;
+        }
+        cached[rb].push_back(Block{p, rb, s, ev});
         return JZ_OK;
     }
 
@@ -187,7 +221,7 @@ struct Pool {
         for (auto& kv : live) cudaFree(kv.first);
         live.clear();
         live_bytes = 0;
-        torn_down = true;
+        torn_down = true;   // late frees (static destructors) of blocks that are already gone are ignored
         for (auto ev : events) cudaEventDestroy(ev);
         events.clear();
         return JZ_OK;
@@ -197,6 +231,20 @@ struct Pool {
 static Pool& pool() {
     static Pool* p = new Pool();  // intentionally leaked: outlives static destructors of callers
     return *p;
+}
+
+static int pool_prepare_device_switch() {
+    Pool& p = pool();
+    std::lock_guard<std::mutex> lk(p.mu);
+    if (!p.live.empty()) return fail(JZ_ERR_ARG, "jz_init: cannot switch device while %zu pool blocks are live", p.live.size());
+    cudaDeviceSynchronize();
+    p.trim_locked();
+    return JZ_OK;
+}
+static void pool_mark_alive() {
+    Pool& p = pool();
+    std::lock_guard<std::mutex> lk(p.mu);
+    p.torn_down = false;   // after jz_shutdown + jz_init, unknown pointers are errors again
 }
 
 unsigned* tickets_for(cudaStream_t s) {

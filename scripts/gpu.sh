@@ -9,6 +9,9 @@
 #   bench         python bench.py (+ --impl reference)
 #   attention     bench_attention (helper kernels + strided-batched GEMM vs the reference's kernels / cuBLAS)
 #   mnist         bench_mnist_step at batch 32 / 8192 / 60000, this backend and the reference's CUDA build
+#   softmax       long-column softmax, with and without the next-column prefetch
+#   dropin        the reference's own programs + test_fusion against this backend (tests/test_dropin_gpu.py)
+#   ncu_config1   source-level ncu of the GEMM with the config-1 chain in its epilogue
 #   ncu_gemm      ncu --set full of the tensor-core GEMM at 1024 / 4096 / 8192 (both modes)
 #   ncu_launches  ncu launch list of the bench command
 #   sanitizer     compute-sanitizer memcheck + racecheck over the GPU tests
@@ -43,6 +46,17 @@ for stage in "$@"; do
         echo "--- batch $b: reference CUDA/cuBLAS build"; MNIST_BATCH=$b timeout -k 5 300 oracle/_ref/cuda/bench_mnist_step 2>&1 | grep -E "bench_mnist_step"
         echo "--- batch $b: reference CUDA/cuBLAS build, NVIDIA_TF32=1"; NVIDIA_TF32=1 MNIST_BATCH=$b timeout -k 5 300 oracle/_ref/cuda/bench_mnist_step 2>&1 | grep -E "bench_mnist_step"
       done 2>&1 | tee gpurun_out/${TAG}_mnist_step.log ;;
+    softmax)
+      { timeout -k 5 300 python scripts/long_softmax_bench.py; JZ_SOFTMAX_NO_PREFETCH=1 timeout -k 5 300 python scripts/long_softmax_bench.py; } 2>&1 | tee gpurun_out/${TAG}_long_column_softmax.log ;;
+    dropin)
+      timeout -k 5 1500 python -m pytest tests/test_dropin_gpu.py -m gpu -q -x --tb=short 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest_dropin.log ;;
+    ncu_config1)
+      # source-level profile of the GEMM with the config-1 chain fused into its epilogue (4096^3, 3xTF32)
+      timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 2 -c 1 -o gpurun_out/${TAG}_config1 -f \
+          python scripts/config1_probe.py > gpurun_out/${TAG}_ncu_config1.log 2>&1
+      tail -3 gpurun_out/${TAG}_ncu_config1.log
+      ncu -i gpurun_out/${TAG}_config1.ncu-rep --page source --csv > gpurun_out/${TAG}_config1_source.csv 2>/dev/null
+      ncu -i gpurun_out/${TAG}_config1.ncu-rep --page raw --csv > gpurun_out/${TAG}_config1_raw.csv 2>/dev/null; wc -c gpurun_out/${TAG}_config1_*.csv ;;
     ncu_gemm)
       timeout -k 5 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 6 -c 12 -o gpurun_out/${TAG}_gemm -f \
           python scripts/gemm_sweep.py ${arg:-1024 4096} > gpurun_out/${TAG}_ncu_gemm.log 2>&1

@@ -277,8 +277,8 @@ def test_gemm_strided_batched_attention_shapes_on_tensor_cores(jz, mode, seq, dh
         jz._lib.check(L.jz_gemm_strided_batched(1, 0, seq, seq, dh, scale, dQ.ptr + 4 * h * dh, dk, stride_qkv,
                                                 dK.ptr + 4 * h * dh, dk, stride_qkv, 0.0,
                                                 scores.ptr + 4 * h * head_attn, seq, stride_attn, batch, md, None))
-        if seq >= 64 and dh >= 32:
-            assert L.jz_gemm_last_path() == 1, "attention members must run on the tcgen05 kernel"
+        if seq * seq * dh >= (1 << 21):
+            assert L.jz_gemm_last_path() == 1, "attention members of >= 2^21 multiply-adds must run on the tcgen05 kernel"
     S = scores.to_host().ravel().reshape(heads, batch, seq, seq)      # [h][b][key j][query i] (column-major seq x seq)
     for h in range(heads):
         for b in range(batch):
