@@ -470,8 +470,8 @@ def run_sharded_gemm(jz, L, args, world, rank, stream, timed, pk):
     modes = ("nccl", "fused", "mcast", "ipc") if world > 1 else ("local",)
     for n in args.sharded_n:
         steps = [("affine", 1.0 / n, 0.0), ("exp",), ("affine", 1.0, 1.0), ("log",), ("affine", FIFTH, 0.0)]
-        a = jz.CM.randn(n, n, seed=21)        # replicated operands: the same bits on every rank (same seed, same stream id)
-        bfull = jz.CM.randn(n, n, seed=22)
+        a = jz.CM.randn(n, n, seed=21, offset=0)        # replicated operands: the same bits on every rank (same seed and stream id)
+        bfull = jz.CM.randn(n, n, seed=22, offset=0)
         j0, j1 = mg.block_range(n, world, rank)
         b_ptr = bfull.ptr + 4 * j0 * n         # this rank's column block: contiguous in column-major storage
         res = {"strong_scaling": True, "flops": 2.0 * n ** 3}

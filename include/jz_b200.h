@@ -244,7 +244,9 @@ int jz_layernorm_forward(float* y, float* xhat, float* inv_std, const float* x, 
 int jz_layernorm_backward(float* dx, const float* dy, const float* gamma, const float* xhat, const float* inv_std,
                           size_t dim, size_t n, jz_stream_t stream);
 
-/* ---- RNG (replaces cuRAND XORWOW, cumatrix.cu:354-420; counter-based Philox4x32-10) */
+/* ---- RNG (replaces cuRAND XORWOW, cumatrix.cu:354-420; counter-based Philox4x32-10).  `offset` selects an independent
+ *      STREAM of the generator (it is the upper half of the Philox counter, not an element offset): the same
+ *      (seed, offset, n) always yields the same values; two draws that must differ need different offsets. */
 int jz_rand_uniform(float* x, size_t n, uint64_t seed, uint64_t offset, jz_stream_t stream);
 int jz_rand_normal(float* x, size_t n, uint64_t seed, uint64_t offset, jz_stream_t stream);
 

@@ -40,6 +40,15 @@ unsigned* tickets_for(cudaStream_t s);
 // temporary workspace from the stream-ordered pool (bytes), released with ws_free
 int ws_alloc(void** p, size_t bytes, cudaStream_t s);
 int ws_free(void* p, cudaStream_t s);
+// scope guard: the workspace goes back to the pool on every exit path (JZ_LAUNCH / JZ_CUDA return early on errors)
+struct WsGuard {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    explicit WsGuard(cudaStream_t stream) : s(stream) {}
+    ~WsGuard() { if (p) ws_free(p, s); }
+    WsGuard(const WsGuard&) = delete;
+    WsGuard& operator=(const WsGuard&) = delete;
+};
 
 }  // namespace jz
 

@@ -536,7 +536,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             v[c] = __fadd_rn(__fmul_rn(s_chain.bias_s1, v[c]), __fmul_rn(s_chain.bias_s2, bv));
                         }
                     }
-                    if (s_chain.n) apply_chain<32>(v, s_chain);
+                    if (s_chain.n) {
+                        // Elementwise program: NOT unrolled over the 32 columns in registers -- that is ~100 KB of
+                        // straight-line code per tile, executed once, and the epilogue then waits on instruction
+                        // fetch (ncu: a third of all samples stalled on no_instruction, profiles/r02_config1_*).  The
+                        // row goes through a per-warp 32 x 32 scratch in the (now idle) operand stages and a compact
+                        // loop applies the program four columns at a time: same per-element arithmetic, same bits.
+                        float* const sw = reinterpret_cast<float*>(gen_base) + e * 1024;
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 32; c++) sw[c * 32 + lane] = v[c];
+                        __syncwarp();
+#pragma unroll 1
+                        for (int c0 = 0; c0 < ncols; c0 += 4) {
+                            float w[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) w[q] = sw[(c0 + q) * 32 + lane];
+                            apply_chain<4>(w, s_chain);
+                            if (row_ok) {
+                                if (args.mc) {
+#pragma unroll
+                                    for (int q = 0; q < 4; q++)
+                                        if (c0 + q < ncols) multimem_st(args.mc + row + (colp + c0 + q) * ldc, w[q]);
+                                } else {
+                                    for (int d = 0; d <= args.n_peers; d++) {
+                                        float* dst = (d == 0 ? Cb : s_peers[d - 1]) + row + (colp + c0) * ldc;
+#pragma unroll
+                                        for (int q = 0; q < 4; q++) {
+                                            if (c0 + q < ncols) *dst = w[q];
+                                            dst += ldc;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     // a warp writes 32 consecutive floats (128 B) per column.  Multi-GPU (fused all-gather): either ONE
                     // multimem.st per element to the multicast image (NVSwitch replicates it into every GPU's C,
                     // this one included), or the local C plus one P2P store per peer image.

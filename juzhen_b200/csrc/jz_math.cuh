@@ -103,9 +103,9 @@ __device__ __forceinline__ void log_tile(float (&v)[N]) {
     if (!special) {
 #pragma unroll
         for (int i = 0; i < N; i++) v[i] = log_main(v[i]);
-    } else {
+    } else {   // rare: decide per element, so that the result of an element never depends on its tile mates
 #pragma unroll  // (a rolled loop would index v[] dynamically and push the whole tile into local memory)
-        for (int i = 0; i < N; i++) v[i] = logf(v[i]);
+        for (int i = 0; i < N; i++) v[i] = log_1ulp(v[i]);
     }
 }
 

@@ -567,17 +567,15 @@ static int reduce_dim0(float* out, const float* a, size_t rows, size_t cols, siz
     chunk_len = (chunk_len + 31) & ~size_t(31);
     nchunks = ceil_div(rows, chunk_len);
     if (cols > 65535) return fail(JZ_ERR_UNSUPPORTED, "reduce: too many long columns");
-    void* partial = nullptr;
-    int rc = ws_alloc(&partial, nchunks * cols * sizeof(float), s);
+    WsGuard wg(s);
+    int rc = ws_alloc(&wg.p, nchunks * cols * sizeof(float), s);
     if (rc != JZ_OK) return rc;
-    float* pf = static_cast<float*>(partial);
+    float* pf = static_cast<float*>(wg.p);
     const dim3 grid((unsigned)nchunks, (unsigned)cols, 1);
     if (vec) JZ_LAUNCH((colreduce_chunk_kernel<Op, true>), grid, 256, 0, s, pf, a, rows, ld, chunk_len, unsigned(nchunks));
     else JZ_LAUNCH((colreduce_chunk_kernel<Op, false>), grid, 256, 0, s, pf, a, rows, ld, chunk_len, unsigned(nchunks));
     // fold: partial is an (nchunks x cols) col-major matrix -> reduce down its columns
-    rc = reduce_dim0<Op>(out, pf, nchunks, cols, nchunks, s);
-    ws_free(partial, s);
-    return rc;
+    return reduce_dim0<Op>(out, pf, nchunks, cols, nchunks, s);
 }
 
 template <class Op>
@@ -609,9 +607,10 @@ static int reduce_dim1(float* out, const float* a, size_t rows, size_t cols, siz
         cpc = ceil_div(cols, nch);
         unsigned* tickets = tickets_for(s);
         if (!tickets) return fail(JZ_ERR_CUDA, "reduce: could not allocate the ticket counters");
-        void* partial = nullptr;
-        int rc = ws_alloc(&partial, (nch / kRowCluster) * rows * sizeof(float), s);
+        WsGuard wg(s);
+        int rc = ws_alloc(&wg.p, (nch / kRowCluster) * rows * sizeof(float), s);
         if (rc != JZ_OK) return rc;
+        void* partial = wg.p;
         cudaLaunchConfig_t cfg;
         std::memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)gx, (unsigned)nch, 1);
@@ -629,25 +628,22 @@ static int reduce_dim1(float* out, const float* a, size_t rows, size_t cols, siz
         cudaError_t e = vec ? cudaLaunchKernelEx(&cfg, rowreduce_kernel<Op, 4, true>, part, a, rows, cols, ld, cpc, out, tickets)
                             : cudaLaunchKernelEx(&cfg, rowreduce_kernel<Op, 1, true>, part, a, rows, cols, ld, cpc, out, tickets);
         ctx().launches.fetch_add(1, std::memory_order_relaxed);
-        ws_free(partial, s);
         if (e != cudaSuccess) return cuda_fail(e, "rowreduce_kernel (cluster) launch");
         return JZ_OK;
     }
     const dim3 grid((unsigned)gx, (unsigned)nchunks, 1);
     float* dst = out;
-    void* partial = nullptr;
+    WsGuard wg(s);
     if (nchunks > 1) {
-        int rc = ws_alloc(&partial, nchunks * rows * sizeof(float), s);
+        int rc = ws_alloc(&wg.p, nchunks * rows * sizeof(float), s);
         if (rc != JZ_OK) return rc;
-        dst = static_cast<float*>(partial);
+        dst = static_cast<float*>(wg.p);
     }
     if (vec) JZ_LAUNCH((rowreduce_kernel<Op, 4, false>), grid, block, smem, s, dst, a, rows, cols, ld, cpc, nullptr, nullptr);
     else JZ_LAUNCH((rowreduce_kernel<Op, 1, false>), grid, block, smem, s, dst, a, rows, cols, ld, cpc, nullptr, nullptr);
     if (nchunks > 1) {
         // partial is rows x nchunks (col-major, ld = rows): fold across its columns
-        int rc = reduce_dim1<Op>(out, dst, rows, nchunks, rows, s);
-        ws_free(partial, s);
-        return rc;
+        return reduce_dim1<Op>(out, dst, rows, nchunks, rows, s);
     }
     return JZ_OK;
 }
@@ -685,31 +681,18 @@ softmax_cluster_kernel(float* out, const float* a, const float* y, size_t rows, 
     const size_t seg = (n4 + CL - 1) / CL;                  // float4 words per CTA
     const size_t lo = size_t(r) * seg, hi = lo + seg < n4 ? lo + seg : n4;
     const size_t ncl = gridDim.x / CL;
-    // the next column's share is copied into shared memory (cp.async, per-thread private slots) while this one is
-    // reduced, exponentiated and stored: see softmax_reg_kernel's PREF
-    extern __shared__ float4 sm_stage[];   // [NV][512]
-    auto prefetch = [&](size_t c) {
-        const float4* col = reinterpret_cast<const float4*>(a + c * ld);
-#pragma unroll
-        for (int q = 0; q < NV; q++) {
-            const size_t i = lo + threadIdx.x + size_t(q) * 512;
-            if (i < hi) cp_async16(&sm_stage[q * 512 + threadIdx.x], col + i);
-        }
-    };
-    if (blockIdx.x / CL < cols) prefetch(blockIdx.x / CL);
     for (size_t c = blockIdx.x / CL; c < cols; c += ncl) {
+        const float4* col = reinterpret_cast<const float4*>(a + c * ld);
         float4 v[NV];
         float m = -1e30f;
-        cp_async_wait_all();
 #pragma unroll
         for (int q = 0; q < NV; q++) {
             const size_t i = lo + threadIdx.x + size_t(q) * 512;
             if (i < hi) {
-                v[q] = sm_stage[q * 512 + threadIdx.x];
+                v[q] = col[i];
                 m = fmaxf(m, fmaxf(fmaxf(v[q].x, v[q].y), fmaxf(v[q].z, v[q].w)));
             }
         }
-        if (c + ncl < cols) prefetch(c + ncl);
         m = warp_reduce<MaxOp>(m);
         if (lane == 0) red[warp] = m;
         __syncthreads();
@@ -764,22 +747,122 @@ softmax_cluster_kernel(float* out, const float* a, const float* y, size_t rows, 
     }
 }
 
+// ---- very long columns (rows > 32768), two passes over GROUPS of columns that stay in L2 between the passes:
+//   pass A  CTA (chunk, column): max m_c and z_c = sum exp(x - m_c) of a chunk of kLongChunk elements (the read that
+//           comes from HBM; the lines stay in the 126 MB L2);
+//   pass B  same grid: folds the column's (m_c, z_c) pairs in chunk order -- M = max m_c, Z = sum z_c * exp(m_c - M) --
+//           and writes exp(x - M) / Z, re-reading the chunk from L2.
+// HBM traffic stays at the algorithmic 8 B/elem as long as a group (kLongGroupBytes of input) survives in L2; no
+// cluster barriers, any column length, every SM busy whatever the column count.
+constexpr int kLongChunk = 8192;                       // elements per CTA: 8 float4 per thread
+constexpr size_t kLongGroupBytes = size_t(40) << 20;   // input bytes per group of columns
+
+__global__ void __launch_bounds__(256) softmax_long_stats_kernel(float2* part, const float* a, size_t rows, size_t ld, size_t col0,
+                                                                 unsigned nchunks) {
+    __shared__ float red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t c = col0 + blockIdx.y, r0 = size_t(blockIdx.x) * kLongChunk;
+    const size_t n4 = (rows - r0 < size_t(kLongChunk) ? rows - r0 : size_t(kLongChunk)) >> 2;
+    const float4* col = reinterpret_cast<const float4*>(a + c * ld + r0);
+    float4 v[8];
+    float m = -1e30f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const size_t i = threadIdx.x + size_t(q) * 256;
+        if (i < n4) {
+            v[q] = col[i];
+            m = fmaxf(m, fmaxf(fmaxf(v[q].x, v[q].y), fmaxf(v[q].z, v[q].w)));
+        }
+    }
+    m = warp_reduce<MaxOp>(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = warp_reduce<MaxOp>(red[lane & 7]);
+    float z = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const size_t i = threadIdx.x + size_t(q) * 256;
+        if (i < n4)
+            z += (expf(__fadd_rn(-m, v[q].x)) + expf(__fadd_rn(-m, v[q].y))) + (expf(__fadd_rn(-m, v[q].z)) + expf(__fadd_rn(-m, v[q].w)));
+    }
+    z = warp_reduce<SumOp>(z);
+    __syncthreads();
+    if (lane == 0) red[warp] = z;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += red[w];
+        part[size_t(blockIdx.y) * nchunks + blockIdx.x] = make_float2(m, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) softmax_long_apply_kernel(float* out, const float* a, const float* y, const float2* part, size_t rows,
+                                                                 size_t ld, size_t col0, unsigned nchunks, int mode, float rnb) {
+    const size_t c = col0 + blockIdx.y, r0 = size_t(blockIdx.x) * kLongChunk;
+    const size_t n4 = (rows - r0 < size_t(kLongChunk) ? rows - r0 : size_t(kLongChunk)) >> 2;
+    const float2* pc = part + size_t(blockIdx.y) * nchunks;
+    float M = -1e30f;
+    for (unsigned q = 0; q < nchunks; q++) M = fmaxf(M, pc[q].x);
+    float Z = 0.0f;
+    for (unsigned q = 0; q < nchunks; q++) Z += __fmul_rn(pc[q].y, expf(__fadd_rn(-M, pc[q].x)));   // chunk order: same in every CTA
+    const float inv = __fdiv_rn(1.0f, Z);
+    const float4* col = reinterpret_cast<const float4*>(a + c * ld + r0);
+    float4* o4 = reinterpret_cast<float4*>(out + c * rows + r0);
+    const float4* y4 = reinterpret_cast<const float4*>(mode == 1 ? y + c * rows + r0 : nullptr);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const size_t i = threadIdx.x + size_t(q) * 256;
+        if (i < n4) {
+            const float4 x = col[i];
+            float4 t;
+            t.x = __fmul_rn(expf(__fadd_rn(-M, x.x)), inv); t.y = __fmul_rn(expf(__fadd_rn(-M, x.y)), inv);
+            t.z = __fmul_rn(expf(__fadd_rn(-M, x.z)), inv); t.w = __fmul_rn(expf(__fadd_rn(-M, x.w)), inv);
+            if (mode == 1) {
+                const float4 u = y4[i];
+                t.x = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-t.x, u.x), 0.0f)), 0.0f);
+                t.y = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-t.y, u.y), 0.0f)), 0.0f);
+                t.z = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-t.z, u.z), 0.0f)), 0.0f);
+                t.w = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-t.w, u.w), 0.0f)), 0.0f);
+            }
+            o4[i] = t;
+        }
+    }
+}
+
+static bool nchunks_ok(size_t rows) { return ceil_div(rows, size_t(kLongChunk)) < (size_t(1) << 31); }
+
+static int launch_softmax_long(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode, float rnb,
+                               cudaStream_t s) {
+    const size_t nchunks = ceil_div(rows, size_t(kLongChunk));
+    size_t group = kLongGroupBytes / (rows * sizeof(float));
+    if (group < 1) group = 1;
+    if (group > 65535) group = 65535;
+    if (group > cols) group = cols;
+    WsGuard wg(s);
+    int rc = ws_alloc(&wg.p, group * nchunks * sizeof(float2), s);
+    if (rc != JZ_OK) return rc;
+    float2* part = static_cast<float2*>(wg.p);
+    for (size_t c0 = 0; c0 < cols; c0 += group) {
+        const size_t g = cols - c0 < group ? cols - c0 : group;
+        const dim3 grid((unsigned)nchunks, (unsigned)g, 1);
+        JZ_LAUNCH(softmax_long_stats_kernel, grid, 256, 0, s, part, a, rows, ld, c0, unsigned(nchunks));
+        JZ_LAUNCH(softmax_long_apply_kernel, grid, 256, 0, s, out, a, y, part, rows, ld, c0, unsigned(nchunks), mode, rnb);
+    }
+    return JZ_OK;
+}
+
 template <int NV, int CL>
 static int launch_softmax_cluster(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode,
                                   float rnb, cudaStream_t s) {
-    constexpr int SMEM = NV * 512 * 16;                       // the prefetch staging: 64 KB (NV = 8) or 128 KB (NV = 16)
-    static bool attr_done = false;
-    if (!attr_done) {
-        JZ_CUDA(cudaFuncSetAttribute(softmax_cluster_kernel<NV, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_done = true;
-    }
-    const size_t slots = size_t(ctx().sm_count) * (NV <= 8 ? 2 : 1) / CL;   // resident CTAs per SM by shared memory
+    // (a cp.async next-column prefetch like softmax_reg_kernel's was tried here: the staging memory halves the resident
+    // CTAs and the kernel got slower, 0.46 -> 0.32 of the copy peak at 65536 rows, profiles/r02b_long_column_softmax.log)
+    const size_t slots = size_t(ctx().sm_count) * 2 / CL;   // ~2 CTAs per SM
     const size_t ncl = cols < slots ? cols : slots;
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(unsigned(ncl * CL), 1, 1);
     cfg.blockDim = dim3(512, 1, 1);
-    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -827,6 +910,9 @@ static int softmax_impl(float* out, const float* a, const float* y, size_t rows,
     const bool vec = aligned16(a) && ld % 4 == 0;
     const bool regs_base = vec && rows % 4 == 0 && aligned16(out) && (mode == 0 || aligned16(y));
     static const bool no_cluster_sm = std::getenv("JZ_SOFTMAX_NO_CLUSTER") != nullptr;
+    static const bool use_cluster_sm = std::getenv("JZ_SOFTMAX_CLUSTER") != nullptr;   // the older DSMEM form, for comparison
+    if (regs_base && rows > 32768 && !use_cluster_sm && !no_cluster_sm && nchunks_ok(rows))
+        return launch_softmax_long(out, a, y, rows, cols, ld, mode, rnb, s);
     if (regs_base && rows > 32768 && rows <= 262144 && !no_cluster_sm) {   // column shared by a cluster (see the kernel)
         const size_t n4 = rows >> 2;
         if (n4 <= 8192) return launch_softmax_cluster<8, 2>(out, a, y, rows, cols, ld, mode, rnb, s);
@@ -853,21 +939,19 @@ static int softmax_impl(float* out, const float* a, const float* y, size_t rows,
             static const bool no_pref = std::getenv("JZ_SOFTMAX_NO_PREFETCH") != nullptr;
             if (n4 <= 1024) JZ_SM_BLOCK(2);
             else if (n4 <= 2048) JZ_SM_BLOCK(4);
-            else if (n4 <= 4096 && (no_pref || cols < 2 * size_t(ctx().sm_count))) JZ_SM_BLOCK(8);
+            else if (n4 <= 4096) JZ_SM_BLOCK(8);       // two CTAs per SM already overlap each other's phases (1.03 of the copy peak)
             else if (no_pref || cols < 2 * size_t(ctx().sm_count)) JZ_SM_BLOCK(16);
             else {
-                // long columns, several per SM: persistent CTAs (as many as stay resident) that prefetch their next column
+                // 16384 < rows <= 32768, one CTA per SM: persistent CTAs that prefetch their next column through shared
+                // memory (0.77 -> 0.84 of the copy peak at 24576 rows, 0.85 -> 0.92 at 32768, profiles/r02b_long_column_softmax.log)
                 static bool attr_done = false;
                 if (!attr_done) {
-                    JZ_CUDA(cudaFuncSetAttribute(softmax_reg_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 512 * 16));
                     JZ_CUDA(cudaFuncSetAttribute(softmax_reg_kernel<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 512 * 16));
                     attr_done = true;
                 }
-                const bool nv8 = n4 <= 4096;
-                const size_t resident = size_t(ctx().sm_count) * (nv8 ? 2 : 1);
+                const size_t resident = size_t(ctx().sm_count);
                 const unsigned pgrid = unsigned(cols < resident ? cols : resident);
-                if (nv8) JZ_LAUNCH((softmax_reg_kernel<8, true, true>), pgrid, 512, 8 * 512 * 16, s, out, a, y, rows, cols, ld, mode, rnb);
-                else JZ_LAUNCH((softmax_reg_kernel<16, true, true>), pgrid, 512, 16 * 512 * 16, s, out, a, y, rows, cols, ld, mode, rnb);
+                JZ_LAUNCH((softmax_reg_kernel<16, true, true>), pgrid, 512, 16 * 512 * 16, s, out, a, y, rows, cols, ld, mode, rnb);
             }
 #undef JZ_SM_BLOCK
         }
@@ -907,16 +991,15 @@ int jz_nrm2(const float* x, size_t n, float* result_host, jz_stream_t stream) {
     const bool vec = aligned16(x);
     const size_t want = ceil_div(vec ? (n >> 2) + 1 : n, size_t(256) * 4);
     const unsigned grid = unsigned(want < cap ? (want ? want : 1) : cap);
-    void* ws = nullptr;
-    int rc = ws_alloc(&ws, grid * sizeof(double) + 16, s);
+    WsGuard wg(s);
+    int rc = ws_alloc(&wg.p, grid * sizeof(double) + 16, s);
     if (rc != JZ_OK) return rc;
-    double* partial = static_cast<double*>(ws);
+    double* partial = static_cast<double*>(wg.p);
     float* dres = reinterpret_cast<float*>(partial + grid);
     JZ_LAUNCH(sumsq_partial_kernel, grid, 256, 0, s, partial, x, n, vec);
     JZ_LAUNCH(nrm2_final_kernel, 1, 256, 0, s, dres, partial, int(grid));
     JZ_CUDA(cudaMemcpyAsync(result_host, dres, sizeof(float), cudaMemcpyDeviceToHost, s));
     JZ_CUDA(cudaStreamSynchronize(s));
-    ws_free(ws, s);
     return JZ_OK;
 }
 

@@ -122,6 +122,12 @@ struct Pool {
     std::vector<cudaEvent_t> events;                        // recycled events
     size_t live_bytes = 0, cached_bytes = 0, n_device_allocs = 0, n_hits = 0;
     bool torn_down = false;  // set by destroy(): late frees from static destructors are then ignored
+    bool have_stream = false, multi_stream = false;
+    cudaStream_t first_stream = nullptr;
+    void note_stream(cudaStream_t s) {
+        if (!have_stream) { have_stream = true; first_stream = s; }
+        else if (s != first_stream) multi_stream = true;
+    }
 
     static size_t round_up(size_t bytes) {
         if (bytes == 0) bytes = 4;  // count==0 -> 1 element (cpp/cumatrix.cuh:71)
@@ -150,14 +156,24 @@ struct Pool {
             for (size_t i = vec.size(); i-- > 0;)
                 if (vec[i].freed_on == s) { pick = i; break; }
             Block b = vec[pick];
+            note_stream(s);
             if (b.freed_on != s) {
-                // another stream: wait for the work that was queued on the freeing stream WHEN the block was released
-                // (the event was recorded then, so later work on that stream is not waited for and the stream need
-                // not exist any more).  On failure the block stays cached and the caller gets a fresh allocation.
-                if (!b.freed_ev || cudaStreamWaitEvent(s, b.freed_ev, 0) != cudaSuccess) {
+                // another stream: wait for the work that was queued on the freeing stream when the block was released.
+                // Once the pool has seen two streams every release records that point (below); blocks released
+                // earlier fall back to an event recorded on the freeing stream now.  On any failure the block stays
+                // cached and the caller gets a fresh allocation -- nothing is lost.
+                cudaEvent_t ev = b.freed_ev;
+                if (!ev) {
+                    if (!events.empty()) { ev = events.back(); events.pop_back(); }
+                    else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
+                    if (ev && cudaEventRecord(ev, b.freed_on) != cudaSuccess) { cudaGetLastError(); events.push_back(ev); ev = nullptr; }
+                    if (ev) vec[pick].freed_ev = ev;
+                }
+                if (!ev || cudaStreamWaitEvent(s, ev, 0) != cudaSuccess) {
                     cudaGetLastError();
                     goto fresh;
                 }
+                b.freed_ev = ev;
             }
             vec.erase(vec.begin() + pick);
             if (b.freed_ev) events.push_back(b.freed_ev);
@@ -169,6 +185,7 @@ struct Pool {
             return JZ_OK;
         }
     fresh:
+        note_stream(s);
         void* p = nullptr;
         cudaError_t e = cudaMalloc(&p, rb);
         if (e != cudaSuccess) {
@@ -201,14 +218,19 @@ struct Pool {
         live.erase(it);
         live_bytes -= rb;
         cached_bytes += rb;
-        // the point in the freeing stream after which the block may be reused from ANOTHER stream
+        // the point in the freeing stream after which the block may be reused from ANOTHER stream: recorded only once
+        // the pool has seen a second stream (an event per release costs a single-stream program -- every
+        // Matrix<CUDAfloat> program -- about a microsecond of host time per temporary for nothing)
+        note_stream(s);
         cudaEvent_t ev = nullptr;
-        if (!events.empty()) { ev = events.back(); events.pop_back(); }
-        else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
-        if (ev && cudaEventRecord(ev, s) != cudaSuccess) {   // e.g. a capturing stream: same-stream reuse only
-            cudaGetLastError();
-            events.push_back(ev);
-            ev = nullptr;
+        if (multi_stream) {
+            if (!events.empty()) { ev = events.back(); events.pop_back(); }
+            else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
+            if (ev && cudaEventRecord(ev, s) != cudaSuccess) {   // e.g. a capturing stream: same-stream reuse only
+                cudaGetLastError();
+                events.push_back(ev);
+                ev = nullptr;
+            }
         }
         cached[rb].push_back(Block{p, rb, s, ev});
         return JZ_OK;

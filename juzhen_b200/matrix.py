@@ -104,16 +104,28 @@ class CM:
         r.ones()
         return r
 
+    # `offset` is the stream id of the counter-based generator (jz_rng.cu).  When it is not given, successive draws
+    # take successive streams, like GPUSampler::offset in the C++ shell: two default-argument calls never return the
+    # same matrix.  Pass seed AND offset for a reproducible draw.
+    _next_stream = 0
+
     @staticmethod
-    def randn(m, n, seed=0, offset=0):
+    def _stream_id(offset):
+        if offset is not None:
+            return int(offset)
+        CM._next_stream += 1
+        return CM._next_stream - 1
+
+    @staticmethod
+    def randn(m, n, seed=0, offset=None):
         r = CM.empty("randn", m, n)
-        check(lib().jz_rand_normal(r.ptr, m * n, seed, offset, _stream))
+        check(lib().jz_rand_normal(r.ptr, m * n, seed, CM._stream_id(offset), _stream))
         return r
 
     @staticmethod
-    def rand(m, n, seed=0, offset=0):
+    def rand(m, n, seed=0, offset=None):
         r = CM.empty("rand", m, n)
-        check(lib().jz_rand_uniform(r.ptr, m * n, seed, offset, _stream))
+        check(lib().jz_rand_uniform(r.ptr, m * n, seed, CM._stream_id(offset), _stream))
         return r
 
     # ---- info

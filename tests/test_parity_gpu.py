@@ -240,6 +240,20 @@ def test_softmax_long_columns_cluster(jz, port, rows):
         assert np.all(np.abs(g - refg) <= 1e-5 * np.abs(refg) + 1e-9)
 
 
+def test_softmax_very_long_columns_several_l2_groups(jz):
+    """rows > 32768 take the two-pass form over groups of columns sized to stay in L2 (jz_reduce.cu: launch_softmax_long):
+    enough columns for several groups, a ragged last chunk and a ragged last group"""
+    rng = np.random.default_rng(99)
+    rows, cols = 40004, 600
+    X = F(rng.standard_normal((rows, cols)) * 2)
+    X64 = X.astype(np.float64)
+    E = np.exp(X64 - X64.max(axis=0, keepdims=True))
+    ref = E / E.sum(axis=0, keepdims=True)
+    got = jz.softmax_cols(jz.CM(X)).to_host()
+    assert np.all(np.abs(got - ref) <= 1e-5 * np.abs(ref) + 1e-30)
+    assert same_bits(jz.softmax_cols(jz.CM(X)).to_host(), got)
+
+
 def test_softmax_composite_through_operators(jz, golden):
     """the reference's own formulation (ml/layer.hpp:254-262) through the mirrored operators,
     including the rank-1 GEMM broadcasts, equals the fused kernel."""
@@ -346,9 +360,11 @@ def test_pool_reuses_exact_size_blocks(jz):
 
 
 def test_rng_moments_and_determinism(jz):
-    a = jz.CM.randn(1000, 1001, seed=1).to_host()      # odd count: no scratch buffer needed
-    b = jz.CM.randn(1000, 1001, seed=1).to_host()
-    c = jz.CM.randn(1000, 1001, seed=2).to_host()
+    a = jz.CM.randn(1000, 1001, seed=1, offset=0).to_host()      # odd count: no scratch buffer needed
+    b = jz.CM.randn(1000, 1001, seed=1, offset=0).to_host()
+    c = jz.CM.randn(1000, 1001, seed=2, offset=0).to_host()
+    d1, d2 = jz.CM.randn(64, 64).to_host(), jz.CM.randn(64, 64).to_host()   # default arguments: successive streams
+    assert not np.array_equal(d1, d2)
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     assert abs(a.mean()) < 5e-3 and abs(a.std() - 1) < 5e-3 and np.isfinite(a).all()
     u = jz.CM.rand(1001, 999, seed=3).to_host()
