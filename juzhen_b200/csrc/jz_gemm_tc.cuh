@@ -541,28 +541,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         // straight-line code per tile, executed once, and the epilogue then waits on instruction
                         // fetch (ncu: a third of all samples stalled on no_instruction, profiles/r02_config1_*).  The
                         // row goes through a per-warp 32 x 32 scratch in the (now idle) operand stages and a compact
-                        // loop applies the program four columns at a time: same per-element arithmetic, same bits.
+                        // loop applies the program eight columns at a time: same per-element arithmetic, same bits.
                         float* const sw = reinterpret_cast<float*>(gen_base) + e * 1024;
                         __syncwarp();
 #pragma unroll
                         for (int c = 0; c < 32; c++) sw[c * 32 + lane] = v[c];
                         __syncwarp();
 #pragma unroll 1
-                        for (int c0 = 0; c0 < ncols; c0 += 4) {
-                            float w[4];
+                        for (int c0 = 0; c0 < ncols; c0 += 8) {   // 8 independent dependency chains per thread per step
+                            float w[8];
 #pragma unroll
-                            for (int q = 0; q < 4; q++) w[q] = sw[(c0 + q) * 32 + lane];
-                            apply_chain<4>(w, s_chain);
+                            for (int q = 0; q < 8; q++) w[q] = sw[(c0 + q) * 32 + lane];
+                            apply_chain<8>(w, s_chain);
                             if (row_ok) {
                                 if (args.mc) {
 #pragma unroll
-                                    for (int q = 0; q < 4; q++)
+                                    for (int q = 0; q < 8; q++)
                                         if (c0 + q < ncols) multimem_st(args.mc + row + (colp + c0 + q) * ldc, w[q]);
                                 } else {
                                     for (int d = 0; d <= args.n_peers; d++) {
                                         float* dst = (d == 0 ? Cb : s_peers[d - 1]) + row + (colp + c0) * ldc;
 #pragma unroll
-                                        for (int q = 0; q < 4; q++) {
+                                        for (int q = 0; q < 8; q++) {
                                             if (c0 + q < ncols) *dst = w[q];
                                             dst += ldc;
                                         }

@@ -747,21 +747,23 @@ softmax_cluster_kernel(float* out, const float* a, const float* y, size_t rows, 
     }
 }
 
-// ---- very long columns (rows > 32768), two passes over GROUPS of columns that stay in L2 between the passes:
-//   pass A  CTA (chunk, column): max m_c and z_c = sum exp(x - m_c) of a chunk of kLongChunk elements (the read that
-//           comes from HBM; the lines stay in the 126 MB L2);
-//   pass B  same grid: folds the column's (m_c, z_c) pairs in chunk order -- M = max m_c, Z = sum z_c * exp(m_c - M) --
-//           and writes exp(x - M) / Z, re-reading the chunk from L2.
-// HBM traffic stays at the algorithmic 8 B/elem as long as a group (kLongGroupBytes of input) survives in L2; no
-// cluster barriers, any column length, every SM busy whatever the column count.
-constexpr int kLongChunk = 8192;                       // elements per CTA: 8 float4 per thread
-constexpr size_t kLongGroupBytes = size_t(40) << 20;   // input bytes per group of columns
+// ---- very long columns (rows > 32768): a column is split into chunks of kLongChunk elements, one CTA each, that meet
+// through global memory.  Every CTA keeps its chunk in registers (read ONCE), publishes its partial (max m_c,
+// z_c = sum exp(x - m_c)), takes a ticket on the column's counter and waits until all chunks of the column have
+// published; then M = max m_c, Z = sum z_c * exp(m_c - M) (chunk order: identical in every CTA) and the chunk is
+// written ONCE as exp(x - m_c) * (exp(m_c - M) / Z).  8 B/elem of HBM traffic for any column length, no cluster
+// barriers, and the whole chip is busy whatever the column count.  The chunks of a column sit in consecutive blocks of
+// one launch and far fewer of them exist than CTAs are resident, so under in-order block dispatch the wait cannot
+// deadlock (same argument as the split-K units of jz_gemm_tc.cuh).
+constexpr int kLongChunk = 8192;   // elements per CTA: 8 float4 per thread
 
-__global__ void __launch_bounds__(256) softmax_long_stats_kernel(float2* part, const float* a, size_t rows, size_t ld, size_t col0,
-                                                                 unsigned nchunks) {
+__global__ void __launch_bounds__(256) softmax_chunks_kernel(float* out, const float* a, const float* y, float2* part, unsigned* tickets,
+                                                             size_t rows, size_t ld, unsigned nchunks, int mode, float rnb) {
     __shared__ float red[8];
+    __shared__ float s_scale;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t c = col0 + blockIdx.y, r0 = size_t(blockIdx.x) * kLongChunk;
+    const unsigned chunk = blockIdx.x % nchunks;
+    const size_t c = blockIdx.x / nchunks, r0 = size_t(chunk) * kLongChunk;
     const size_t n4 = (rows - r0 < size_t(kLongChunk) ? rows - r0 : size_t(kLongChunk)) >> 2;
     const float4* col = reinterpret_cast<const float4*>(a + c * ld + r0);
     float4 v[8];
@@ -782,42 +784,49 @@ __global__ void __launch_bounds__(256) softmax_long_stats_kernel(float2* part, c
 #pragma unroll
     for (int q = 0; q < 8; q++) {
         const size_t i = threadIdx.x + size_t(q) * 256;
-        if (i < n4)
-            z += (expf(__fadd_rn(-m, v[q].x)) + expf(__fadd_rn(-m, v[q].y))) + (expf(__fadd_rn(-m, v[q].z)) + expf(__fadd_rn(-m, v[q].w)));
+        if (i < n4) {
+            v[q].x = expf(__fadd_rn(-m, v[q].x)); v[q].y = expf(__fadd_rn(-m, v[q].y));
+            v[q].z = expf(__fadd_rn(-m, v[q].z)); v[q].w = expf(__fadd_rn(-m, v[q].w));
+            z += (v[q].x + v[q].y) + (v[q].z + v[q].w);
+        }
     }
     z = warp_reduce<SumOp>(z);
     __syncthreads();
     if (lane == 0) red[warp] = z;
     __syncthreads();
+    float2* const pc = part + c * nchunks;
     if (threadIdx.x == 0) {
         float t = 0.0f;
 #pragma unroll
         for (int w = 0; w < 8; w++) t += red[w];
-        part[size_t(blockIdx.y) * nchunks + blockIdx.x] = make_float2(m, t);
+        __stcg(pc + chunk, make_float2(m, t));
+        __threadfence();
+        atomicAdd(tickets + c, 1u);
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(tickets + c) : "memory");
+            if (seen < nchunks) __nanosleep(40);
+        } while (seen < nchunks);
+        float M = -1e30f;
+        for (unsigned q = 0; q < nchunks; q++) M = fmaxf(M, __ldcg(pc + q).x);
+        float Z = 0.0f;
+        for (unsigned q = 0; q < nchunks; q++) {
+            const float2 p = __ldcg(pc + q);
+            Z += __fmul_rn(p.y, expf(__fadd_rn(-M, p.x)));
+        }
+        s_scale = __fmul_rn(expf(__fadd_rn(-M, m)), __fdiv_rn(1.0f, Z));
     }
-}
-
-__global__ void __launch_bounds__(256) softmax_long_apply_kernel(float* out, const float* a, const float* y, const float2* part, size_t rows,
-                                                                 size_t ld, size_t col0, unsigned nchunks, int mode, float rnb) {
-    const size_t c = col0 + blockIdx.y, r0 = size_t(blockIdx.x) * kLongChunk;
-    const size_t n4 = (rows - r0 < size_t(kLongChunk) ? rows - r0 : size_t(kLongChunk)) >> 2;
-    const float2* pc = part + size_t(blockIdx.y) * nchunks;
-    float M = -1e30f;
-    for (unsigned q = 0; q < nchunks; q++) M = fmaxf(M, pc[q].x);
-    float Z = 0.0f;
-    for (unsigned q = 0; q < nchunks; q++) Z += __fmul_rn(pc[q].y, expf(__fadd_rn(-M, pc[q].x)));   // chunk order: same in every CTA
-    const float inv = __fdiv_rn(1.0f, Z);
-    const float4* col = reinterpret_cast<const float4*>(a + c * ld + r0);
+    __syncthreads();
+    const float scale = s_scale;
     float4* o4 = reinterpret_cast<float4*>(out + c * rows + r0);
     const float4* y4 = reinterpret_cast<const float4*>(mode == 1 ? y + c * rows + r0 : nullptr);
 #pragma unroll
     for (int q = 0; q < 8; q++) {
         const size_t i = threadIdx.x + size_t(q) * 256;
         if (i < n4) {
-            const float4 x = col[i];
             float4 t;
-            t.x = __fmul_rn(expf(__fadd_rn(-M, x.x)), inv); t.y = __fmul_rn(expf(__fadd_rn(-M, x.y)), inv);
-            t.z = __fmul_rn(expf(__fadd_rn(-M, x.z)), inv); t.w = __fmul_rn(expf(__fadd_rn(-M, x.w)), inv);
+            t.x = __fmul_rn(v[q].x, scale); t.y = __fmul_rn(v[q].y, scale);
+            t.z = __fmul_rn(v[q].z, scale); t.w = __fmul_rn(v[q].w, scale);
             if (mode == 1) {
                 const float4 u = y4[i];
                 t.x = __fadd_rn(__fmul_rn(rnb, __fadd_rn(-__fadd_rn(-t.x, u.x), 0.0f)), 0.0f);
@@ -830,25 +839,22 @@ __global__ void __launch_bounds__(256) softmax_long_apply_kernel(float* out, con
     }
 }
 
-static bool nchunks_ok(size_t rows) { return ceil_div(rows, size_t(kLongChunk)) < (size_t(1) << 31); }
+static bool nchunks_ok(size_t rows, size_t cols) {
+    const size_t nchunks = ceil_div(rows, size_t(kLongChunk));
+    return nchunks <= 256 && nchunks * cols < (size_t(1) << 31);   // a column's CTAs must all fit on the chip at once
+}
 
 static int launch_softmax_long(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode, float rnb,
                                cudaStream_t s) {
     const size_t nchunks = ceil_div(rows, size_t(kLongChunk));
-    size_t group = kLongGroupBytes / (rows * sizeof(float));
-    if (group < 1) group = 1;
-    if (group > 65535) group = 65535;
-    if (group > cols) group = cols;
+    const size_t ticket_bytes = (cols * sizeof(unsigned) + 511) & ~size_t(511);
     WsGuard wg(s);
-    int rc = ws_alloc(&wg.p, group * nchunks * sizeof(float2), s);
+    int rc = ws_alloc(&wg.p, ticket_bytes + cols * nchunks * sizeof(float2), s);
     if (rc != JZ_OK) return rc;
-    float2* part = static_cast<float2*>(wg.p);
-    for (size_t c0 = 0; c0 < cols; c0 += group) {
-        const size_t g = cols - c0 < group ? cols - c0 : group;
-        const dim3 grid((unsigned)nchunks, (unsigned)g, 1);
-        JZ_LAUNCH(softmax_long_stats_kernel, grid, 256, 0, s, part, a, rows, ld, c0, unsigned(nchunks));
-        JZ_LAUNCH(softmax_long_apply_kernel, grid, 256, 0, s, out, a, y, part, rows, ld, c0, unsigned(nchunks), mode, rnb);
-    }
+    unsigned* tickets = static_cast<unsigned*>(wg.p);
+    float2* part = reinterpret_cast<float2*>(static_cast<char*>(wg.p) + ticket_bytes);
+    JZ_CUDA(cudaMemsetAsync(tickets, 0, ticket_bytes, s));
+    JZ_LAUNCH(softmax_chunks_kernel, unsigned(nchunks * cols), 256, 0, s, out, a, y, part, tickets, rows, ld, unsigned(nchunks), mode, rnb);
     return JZ_OK;
 }
 
@@ -911,7 +917,7 @@ static int softmax_impl(float* out, const float* a, const float* y, size_t rows,
     const bool regs_base = vec && rows % 4 == 0 && aligned16(out) && (mode == 0 || aligned16(y));
     static const bool no_cluster_sm = std::getenv("JZ_SOFTMAX_NO_CLUSTER") != nullptr;
     static const bool use_cluster_sm = std::getenv("JZ_SOFTMAX_CLUSTER") != nullptr;   // the older DSMEM form, for comparison
-    if (regs_base && rows > 32768 && !use_cluster_sm && !no_cluster_sm && nchunks_ok(rows))
+    if (regs_base && rows > 32768 && !use_cluster_sm && !no_cluster_sm && nchunks_ok(rows, cols))
         return launch_softmax_long(out, a, y, rows, cols, ld, mode, rnb, s);
     if (regs_base && rows > 32768 && rows <= 262144 && !no_cluster_sm) {   // column shared by a cluster (see the kernel)
         const size_t n4 = rows >> 2;

@@ -240,9 +240,9 @@ def test_softmax_long_columns_cluster(jz, port, rows):
         assert np.all(np.abs(g - refg) <= 1e-5 * np.abs(refg) + 1e-9)
 
 
-def test_softmax_very_long_columns_several_l2_groups(jz):
-    """rows > 32768 take the two-pass form over groups of columns sized to stay in L2 (jz_reduce.cu: launch_softmax_long):
-    enough columns for several groups, a ragged last chunk and a ragged last group"""
+def test_softmax_very_long_columns_chunked(jz):
+    """rows > 32768: a column is split into register-resident chunks, one CTA each, that meet through a ticket in global
+    memory (jz_reduce.cu: softmax_chunks_kernel); many more column-chunks than resident CTAs, a ragged last chunk"""
     rng = np.random.default_rng(99)
     rows, cols = 40004, 600
     X = F(rng.standard_normal((rows, cols)) * 2)
