@@ -16,6 +16,7 @@
 #   ncu_launches  ncu launch list of the bench command
 #   sanitizer     compute-sanitizer memcheck + racecheck over the GPU tests
 #   mg:N          N-GPU parity worker + torchrun bench (call gpurun with --gpus N)
+#   mgquick:N     parity worker (all gather modes) + C++ sharded-dot test + a short torchrun bench with the sharded GEMM block
 #   mgcpp:N       the C++ multi-process sharded-dot test over the jz_mg_* ABI
 TAG=${JZ_TAG:-r02}
 mkdir -p gpurun_out
@@ -78,6 +79,17 @@ for stage in "$@"; do
       timeout -k 5 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
           bench.py --gpus $N --steps 10 --warmup 3 2>gpurun_out/${TAG}_bench_${N}gpu.err | tail -1 | tee gpurun_out/${TAG}_bench_${N}gpu.json | cut -c1-300
       tail -5 gpurun_out/${TAG}_bench_${N}gpu.err ;;
+    mgquick)
+      N=${arg:-2}
+      timeout -k 5 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+          tests/_mg_gpu_worker.py 2>gpurun_out/${TAG}_mg${N}_worker.err | tail -40 | tee gpurun_out/${TAG}_mg${N}_parity.log
+      tail -5 gpurun_out/${TAG}_mg${N}_worker.err
+      timeout -k 5 300 build/dropin/bin/test_mg_dot $N 2>&1 | tail -20 | tee gpurun_out/${TAG}_mgcpp${N}.log
+      timeout -k 5 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+          bench.py --gpus $N --steps 6 --warmup 3 --no-mnist --gemm-n 4096 2>gpurun_out/${TAG}_benchq_${N}gpu.err | tail -1 | tee gpurun_out/${TAG}_benchq_${N}gpu.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('value',d['value'],'e2e',d['e2e']['value']); print(json.dumps(d['sharded_gemm'],indent=1)); print(d['sharded_colsum'])"
+      tail -5 gpurun_out/${TAG}_benchq_${N}gpu.err ;;
     mgcpp)
       N=${arg:-2}
       timeout -k 5 300 build/dropin/bin/test_mg_dot $N 2>&1 | tail -20 | tee gpurun_out/${TAG}_mgcpp${N}.log ;;
