@@ -141,6 +141,8 @@ int jz_max(float* out, const float* a, size_t rows, size_t cols, size_t ld, int 
 int jz_softmax_cols(float* out, const float* a, size_t rows, size_t cols, size_t ld, jz_stream_t stream);
 /* softmax-CE head gradient  G = -(Y - softmax(X)) / nb  (LogisticLayer::grad, ml/layer.hpp:252-264) */
 int jz_softmax_ce_grad(float* out, const float* x, const float* y, size_t rows, size_t cols, float nb, jz_stream_t stream);
+/* same with the factor given as it reaches the kernel: G = ((-(Y - softmax(X))) + 0) * rnb + 0, rnb = (float)(1.0/nb) */
+int jz_softmax_ce_grad_scaled(float* out, const float* x, const float* y, size_t rows, size_t cols, float rnb, jz_stream_t stream);
 int jz_nrm2(const float* x, size_t n, float* result_host, jz_stream_t stream);          /* cublasSnrm2, cumatrix.cu:168-175 (syncs) */
 
 /* broadcast idioms the reference spells as rank-1 GEMMs (b*ones(1,N), ones(m,1)*v):

@@ -73,6 +73,7 @@ _SIGS = {
     "jz_max": (c_int, [_F, _F, c_size_t, c_size_t, c_size_t, c_int, _S]),
     "jz_softmax_cols": (c_int, [_F, _F, c_size_t, c_size_t, c_size_t, _S]),
     "jz_softmax_ce_grad": (c_int, [_F, _F, _F, c_size_t, c_size_t, c_float, _S]),
+    "jz_softmax_ce_grad_scaled": (c_int, [_F, _F, _F, c_size_t, c_size_t, c_float, _S]),
     "jz_nrm2": (c_int, [_F, c_size_t, POINTER(c_float), _S]),
     "jz_add_bcast": (c_int, [_F, _F, c_size_t, c_size_t, _F, c_int, c_float, c_float, _S]),
     "jz_outer": (c_int, [_F, c_size_t, _F, c_size_t, _F, c_size_t, _S]),

@@ -105,7 +105,61 @@ static void run_generator(const Producer& p, float* out, size_t count) {
     else JZ_DO(jz_rand_uniform(out, count, p.seed, p.offset, S()));
 }
 
+// ---- the column-softmax head, stage by stage (see Producer::Kind).  Each function computes its stage from `src` with
+//      the kernels the eager path would have used, so a stage that IS read mid-way costs what it always cost.
+static void run_colmax(const Producer& p, float* out) {
+    p.src->materialize();
+    JZ_DO(jz_max(out, p.src->ptr, p.rows, p.cols, p.rows ? p.rows : 1, 0, S()));
+}
+static void run_shifted(const Producer& p, float* out) {   // x - colmax(x)
+    p.src->materialize();
+    float* mx = reinterpret_cast<float*>(Memory<CUDAfloat>::allocate(p.cols));
+    JZ_DO(jz_max(mx, p.src->ptr, p.rows, p.cols, p.rows ? p.rows : 1, 0, S()));
+    JZ_DO(jz_add_bcast(out, p.src->ptr, p.rows, p.cols, mx, 0, 1.0f, -1.0f, S()));
+    Memory<CUDAfloat>::free(reinterpret_cast<CUDAfloat*>(mx));
+}
+static void run_colsumexp(const Producer& p, float* out) {   // sum_i exp(x_ij - colmax_j)
+    float* e = reinterpret_cast<float*>(Memory<CUDAfloat>::allocate(p.rows * p.cols));
+    run_shifted(p, e);
+    JZ_DO(jz_unary(JZ_EXP, e, e, p.rows * p.cols, S()));
+    JZ_DO(jz_sum(out, e, p.rows, p.cols, p.rows ? p.rows : 1, 0, S()));
+    Memory<CUDAfloat>::free(reinterpret_cast<CUDAfloat*>(e));
+}
+// softmax(src) [* ax_s1 + ax_s2 * other], then the pending program.  The loss-gradient form -(Y - S)/nb
+// (LogisticLayer::grad, ml/layer.hpp:263) is ONE kernel; anything else is the softmax kernel plus the generic passes.
+static void run_softmax(Producer& p, float* out, std::vector<jz_step>& prog) {
+    p.src->materialize();
+    const size_t n = p.rows * p.cols;
+    if (p.other) {
+        p.other->materialize();
+        const bool ce = p.ax_s1 == -1.0f && p.ax_s2 == 1.0f && prog.size() == 2 && prog[0].kind == JZ_STEP_AFFINE && prog[0].s1 == -1.0f &&
+                        prog[0].a == 0.0f && prog[1].kind == JZ_STEP_AFFINE && prog[1].a == 0.0f;
+        if (ce) {
+            JZ_DO(jz_softmax_ce_grad_scaled(out, p.src->ptr, p.other->ptr, p.rows, p.cols, prog[1].s1, S()));
+            prog.clear();
+            return;
+        }
+        JZ_DO(jz_softmax_cols(out, p.src->ptr, p.rows, p.cols, p.rows ? p.rows : 1, S()));
+        JZ_DO(jz_axpby(out, out, p.other->ptr, n, p.ax_s1, p.ax_s2, S()));
+    } else {
+        JZ_DO(jz_softmax_cols(out, p.src->ptr, p.rows, p.cols, p.rows ? p.rows : 1, S()));
+    }
+}
+
 void Storage::materialize() {
+    if (producer && producer->kind >= Producer::COLMAX) {
+        std::unique_ptr<Producer> p = std::move(producer);
+        std::vector<jz_step> prog;
+        prog.swap(pending);
+        switch (p->kind) {
+            case Producer::COLMAX: run_colmax(*p, ptr); break;
+            case Producer::SHIFTED: run_shifted(*p, ptr); break;
+            case Producer::COLSUMEXP: run_colsumexp(*p, ptr); break;
+            default: run_softmax(*p, ptr, prog); break;
+        }
+        if (!prog.empty()) run_program(ptr, ptr, count, prog);
+        return;
+    }
     if (producer && (producer->kind == Producer::FILL || producer->kind == Producer::RAND)) {
         std::unique_ptr<Producer> p = std::move(producer);
         run_generator(*p, ptr, count);   // then the pending in-place program, below
@@ -438,6 +492,23 @@ bool Matrix<CUDAfloat>::add_broadcast(const Matrix<CUDAfloat>& B, float s1, floa
     // this = s1*(u 1^T) + s2*B, this being the not-yet-computed product: one pass from B into this buffer
     if (StoragePtr vec = deferred_broadcast(*mine, numrow, numcol, dim)) {
         if (vec == theirs || !mine->lazy_ok()) return false;
+        // X - ones(K,1) * colmax(X) with the column max itself still deferred: define "X shifted by its column max"
+        // (first stage of the softmax head, Producer::SHIFTED) instead of running the max and the broadcast now
+        if (dim == 0 && s1 == -1.0f && s2 == 1.0f && vec->producer && vec->producer->kind == Producer::COLMAX && vec->pending.empty() &&
+            vec->producer->src == theirs && theirs->lazy_ok() && vec->producer->rows == numrow && vec->producer->cols == numcol) {
+            mine->flush_readers();
+            if (mine->producer && mine->producer->kind == Producer::GEMM) {
+                std::unique_ptr<Producer> p(new Producer());
+                p->kind = Producer::SHIFTED;
+                p->src = theirs;
+                p->rows = numrow;
+                p->cols = numcol;
+                mine->producer = std::move(p);
+                mine->konst_known = false;
+                jzb200::add_reader(theirs, mine);
+                return true;
+            }
+        }
         const float* b = B.dev();
         mine->flush_readers();
         if (!mine->producer) return false;   // a deferred reader needed the product itself after all
@@ -453,6 +524,21 @@ bool Matrix<CUDAfloat>::add_broadcast(const Matrix<CUDAfloat>& B, float s1, floa
 void Matrix<CUDAfloat>::add(const Matrix<CUDAfloat>& B, float s1, float s2) {
     require_same_shape(*this, B);
     if (add_broadcast(B, s1, s2)) return;
+    {   // Y - softmax(X) with the softmax still deferred: it becomes part of the softmax pass (Producer::SOFTMAX)
+        jzb200::Storage& st = store();
+        Producer* p = st.producer.get();
+        if (p && p->kind == Producer::SOFTMAX && !p->other && st.pending.empty() && st.lazy_ok() && !transpose && !B.transpose &&
+            B.elements.storage() != elements.storage() && B.elements.storage() != p->src) {
+            st.flush_readers();
+            if (st.producer.get() == p) {
+                p->other = B.elements.storage();
+                p->ax_s1 = s1;
+                p->ax_s2 = s2;
+                jzb200::add_reader(B.elements.storage(), elements.storage());
+                return;
+            }
+        }
+    }
     const float* b = B.dev();  // before wdev(): B may be a deferred view of this very storage
     float* x = wdev();
     if (transpose == B.transpose) JZ_DO(jz_axpby(x, x, b, count(), s1, s2, S()));
@@ -505,6 +591,21 @@ Matrix<CUDAfloat> sum(const Matrix<CUDAfloat>& M, int dim) {
     const bool down_physical_columns = (dim == 0) != M.transpose;
     const size_t len = down_physical_columns ? M.numcol : M.numrow;
     Matrix<CUDAfloat> R(Matrix<CUDAfloat>::Raw{}, "sumM", len, 1, dim == 0);
+    {   // sum(exp(X - colmax), 0) with the shifted matrix still deferred: the softmax denominators, also deferred
+        jzb200::Storage& st = M.store();
+        const Producer* p = st.producer.get();
+        if (dim == 0 && !M.transpose && p && p->kind == Producer::SHIFTED && st.pending.size() == 1 && st.pending[0].kind == JZ_EXP &&
+            st.lazy_ok()) {
+            std::unique_ptr<Producer> q(new Producer());
+            q->kind = Producer::COLSUMEXP;
+            q->src = p->src;
+            q->rows = p->rows;
+            q->cols = p->cols;
+            R.store().producer = std::move(q);
+            jzb200::add_reader(p->src, R.elements.storage());
+            return R;
+        }
+    }
     JZ_DO(jz_sum(R.store().ptr, M.dev(), M.numrow, M.numcol, M.numrow ? M.numrow : 1, down_physical_columns ? 0 : 1, S()));
     return R;
 }
@@ -540,9 +641,41 @@ Matrix<CUDAfloat> hadmd(const Matrix<CUDAfloat>& M1, const Matrix<CUDAfloat>& M2
                              M2.numrow, 1, S()));
     return R;
 }
+// E / Z of the softmax head: M1 = exp(X - colmax) still deferred, M2 = 1 / (ones(K,1) * sum(E,0)) still deferred -> M2's
+// storage is redefined as softmax(X) (Producer::SOFTMAX), nothing runs
+static bool define_softmax(const Matrix<CUDAfloat>& M1, Matrix<CUDAfloat>& M2, jzb200::Storage& s1, jzb200::Storage& s2,
+                           const StoragePtr& s2ptr) {
+    const Producer* e = s1.producer.get();
+    const Producer* g = s2.producer.get();
+    if (!e || !g || e->kind != Producer::SHIFTED || g->kind != Producer::GEMM || !s1.lazy_ok() || !s2.lazy_ok()) return false;
+    if (s1.pending.size() != 1 || s1.pending[0].kind != JZ_EXP) return false;
+    if (s2.pending.size() != 1 || s2.pending[0].kind != JZ_STEP_ELEMINV || s2.pending[0].s1 != 1.0f) return false;
+    if (g->k != 1 || g->bias || g->m != e->rows || g->n != e->cols) return false;
+    const jzb200::Storage& ones = *g->a;
+    if (!(ones.konst_known && ones.konst == 1.0f && ones.pending.empty())) return false;
+    const jzb200::Storage& den = *g->b;
+    if (!den.producer || den.producer->kind != Producer::COLSUMEXP || !den.pending.empty() || den.producer->src != e->src) return false;
+    s2.flush_readers();
+    if (s2.producer.get() != g) return false;
+    std::unique_ptr<Producer> p(new Producer());
+    p->kind = Producer::SOFTMAX;
+    p->src = e->src;
+    p->rows = e->rows;
+    p->cols = e->cols;
+    s2.pending.clear();
+    s2.producer = std::move(p);
+    s2.konst_known = false;
+    jzb200::add_reader(s2.producer->src, s2ptr);
+    (void)M1; (void)M2;
+    return true;
+}
+
 Matrix<CUDAfloat> hadmd(const Matrix<CUDAfloat>& M1, Matrix<CUDAfloat>&& M2) {
     require_same_shape(M1, M2);
     if (M1.transpose != M2.transpose) return hadmd(M1, static_cast<const Matrix<CUDAfloat>&>(M2));
+    if (!M1.transpose && M1.elements.storage() != M2.elements.storage() &&
+        define_softmax(M1, M2, M1.store(), M2.store(), M2.elements.storage()))
+        return std::move(M2);
     const float* other = M1.dev();
     float* x = M2.wdev();
     JZ_DO(jz_hadamard(x, x, other, M1.count(), S()));

@@ -28,6 +28,7 @@
 #include <jz_b200.h>
 
 #include <stdexcept>
+#include <type_traits>
 
 #include "jz_lazy.hpp"
 
@@ -290,10 +291,55 @@ __global__ void __launch_bounds__(128) functor_reduce_kernel(Function func, floa
 
 }  // namespace jzb200
 
+namespace jzb200 {
+// Is this reduce functor "the maximum of the vector, floored at -1e30" -- the one LogisticLayer::grad / eval use
+// (ml/layer.hpp:254-259)?  The functor is opaque, but a __host__ __device__ extended lambda can be CALLED on the host:
+// probe it with a few vectors (including the empty one for its initial value) and compare with that definition.  jz_max
+// computes exactly this (same floor), so a functor that passes may be replaced by the deferred column-max stage of the
+// softmax head; a functor that is device-only, or fails any probe, runs as the opaque kernel it always was.
+template <class Function>
+inline bool functor_is_floored_max(Function& func) {
+#if defined(__CUDACC_EXTENDED_LAMBDA__)
+    // captureless lambdas only: a functor with captures may hold DEVICE pointers (examples/knn.cu:84 does) and must
+    // never be run on the host
+    if constexpr (__nv_is_extended_host_device_lambda_closure_type(Function) && std::is_empty<Function>::value) {
+        static const float probes[4][6] = {{-3.5f, 2.25f, 2.0f, -7.0f, 0.5f, 1.0f}, {-9.0f, -4.0f, -4.5f, -100.0f, -5.0f, -6.0f},
+                                           {0.0f, -0.0f, 1e-30f, -1e-30f, 0.0f, 0.0f}, {7.0f, 7.0f, 7.0f, 7.0f, 7.0f, 8.0f}};
+        static const float want[4] = {2.25f, -4.0f, 1e-30f, 8.0f};
+        for (int t = 0; t < 4; t++) {
+            float v[6], out[1] = {123.0f};
+            for (int i = 0; i < 6; i++) v[i] = probes[t][i];
+            func(v, out, 6, 1);
+            if (out[0] != want[t]) return false;
+            for (int i = 0; i < 6; i++)
+                if (v[i] != probes[t][i]) return false;   // a functor that scribbles on its input is not a pure max
+        }
+        float none[1] = {0.0f}, out[1] = {123.0f};
+        func(none, out, 0, 1);
+        return out[0] == -1e30f;
+    }
+#endif
+    (void)func;
+    return false;
+}
+}  // namespace jzb200
+
 template <class Function>
 Matrix<CUDAfloat> reduce(Function func, const Matrix<CUDAfloat>& M, int dim, int k) {
     // the functor walks PHYSICAL columns; reducing along the other direction needs the transpose in memory
     const bool along_physical_columns = (dim == 0) != M.transpose;
+    if (k == 1 && dim == 0 && !M.transpose && M.numrow > 0 && M.numcol > 0 && M.store().lazy_ok() && jzb200::functor_is_floored_max(func)) {
+        // column maxima, DEFINED but not computed: first stage of the softmax head (jz_lazy.hpp, Producer::COLMAX)
+        Matrix<CUDAfloat> result(Matrix<CUDAfloat>::Raw{}, "resM", 1, M.numcol, false);
+        std::unique_ptr<jzb200::Producer> p(new jzb200::Producer());
+        p->kind = jzb200::Producer::COLMAX;
+        p->src = M.elements.storage();
+        p->rows = M.numrow;
+        p->cols = M.numcol;
+        result.store().producer = std::move(p);
+        jzb200::add_reader(M.elements.storage(), result.elements.storage());
+        return result;
+    }
     if (along_physical_columns) {
         Matrix<CUDAfloat> result(Matrix<CUDAfloat>::Raw{}, "resM", k, M.numcol, false);
         JZ_DO(jz_fill(result.dev(), result.count(), 0.0f, jz_cpp_stream()));  // functors may accumulate into vdes

@@ -35,7 +35,11 @@ struct Storage;
 using StoragePtr = std::shared_ptr<Storage>;
 
 struct Producer {
-    enum Kind { GEMM, MAP, FILL, RAND } kind = MAP;
+    // COLMAX .. SOFTMAX: the column-softmax head the reference spells with a dozen operators (LogisticLayer::grad,
+    // ml/layer.hpp:252-264): mx = reduce(max, X, 0) -> X - 1*mx -> exp -> sum(.,0) -> 1*sum -> E / Z -> Y - S -> -(.)/nb.
+    // Each stage is DEFINED here without running; when the chain completes, one jz_softmax_cols(-_axpby) pass computes
+    // it from X.  A stage somebody reads in the meantime materialises on its own (see cumatrix.cu).
+    enum Kind { GEMM, MAP, FILL, RAND, COLMAX, SHIFTED, COLSUMEXP, SOFTMAX } kind = MAP;
     // GEMM: C(m x n) = op(A)(m x k) * op(B)(k x n), column-major, lda/ldb = physical rows
     StoragePtr a, b;
     int ta = 0, tb = 0;
@@ -47,7 +51,12 @@ struct Producer {
     int bias_dim = 0;
     float bias_s1 = 1.0f, bias_s2 = 0.0f;
     // MAP: out[i] = steps(src[i]) over the flat physical buffer
+    // COLMAX (1 x cols) / SHIFTED, SOFTMAX (rows x cols) / COLSUMEXP (cols): functions of the plain rows x cols matrix `src`
     StoragePtr src;
+    size_t rows = 0, cols = 0;
+    // SOFTMAX only: value = ax_s1 * softmax(src) + ax_s2 * other when `other` is set (the Y - S of the loss gradient)
+    StoragePtr other;
+    float ax_s1 = 1.0f, ax_s2 = 0.0f;
     std::vector<jz_step> steps;
     // FILL: every element = value.  RAND: counter-based stream (seed, offset) fixed when the matrix was made,
     // so the values do not depend on when -- or whether -- the kernel runs.

@@ -289,6 +289,57 @@ int compute() {
         check(rel_fro(got2, d_tanh(W * x + b * Matrix<float>::ones(1, N))) < 1e-5f, "a bias modified after the deferral does not leak into it");
     }
 
+    // (14c) the softmax-CE head exactly as LogisticLayer::grad spells it (ml/layer.hpp:252-264): every stage is deferred and the
+    //       whole expression is ONE kernel; reading an intermediate mid-way falls back to the stage-by-stage kernels
+    {
+        const size_t K = 10, N = 96, nb = 32;
+        auto X = Matrix<float>::randn(K, N) * 3.0, Yh = Matrix<float>::zeros(K, N);
+        for (size_t j = 0; j < N; j++) Yh.elem(j % K, j) = 1.0f;
+        CM dX(X), dY(Yh), oneK1("oneK1", K, 1);
+        oneK1.ones();
+        Matrix<float> hone("one", K, 1);
+        hone.ones();
+        auto maxf = [] __GPU_CPU__(float* v, float* vdes, int lenv, int) {
+            float m = -1e30f;
+            for (int i = 0; i < lenv; i++) m = m > v[i] ? m : v[i];
+            vdes[0] = m;
+        };
+        auto head = [&](auto& in, auto& one, auto& out) {
+            auto mx = reduce(maxf, in, 0, 1);
+            auto shifted = in - one * mx;
+            auto E = exp(std::move(shifted));
+            auto Z = one * sum(E, 0);
+            return -(out - E / std::move(Z)) / (double)nb;
+        };
+        jz_sync(nullptr);
+        const unsigned long long before = jz_launch_count();
+        CM G = head(dX, oneK1, dY);
+        Matrix<float> got = G.to_host();   // (not in the bitwise dump: the fused kernel sums a column in another order than the composite)
+        const unsigned long long launches = jz_launch_count() - before;
+        Matrix<float> want = head(X, hone, Yh);
+        std::cout << "    softmax-CE head launches: " << launches << ", max abs diff vs CPU " << max_abs_diff(got, want) << std::endl;
+        check(max_abs_diff(got, want) < 1e-7f, "softmax-CE head matches the CPU path");
+        const char* eager = std::getenv("JZ_EAGER");
+        if (!(eager && *eager && std::string(eager) != "0")) check(launches == 1, "fused: the whole head is one kernel");
+        // an intermediate that is read: E is looked at before the division
+        auto mx = reduce(maxf, dX, 0, 1);
+        auto shifted = dX - oneK1 * mx;
+        auto E = exp(std::move(shifted));
+        Matrix<float> Eh = E.to_host();
+        auto Z = oneK1 * sum(E, 0);
+        CM S = E / std::move(Z);
+        Matrix<float> hmx = reduce(maxf, X, 0, 1);
+        Matrix<float> hE = exp(X - hone * hmx);
+        Matrix<float> hS = hE / (hone * sum(hE, 0));
+        check(max_abs_diff(Eh, hE) < 1e-6f && max_abs_diff(S.to_host(), hS) < 1e-6f && max_abs_diff(mx.to_host(), hmx) == 0.0f,
+              "stages of the head read mid-way (column max, exp(shifted), softmax) match the CPU path");
+        // the source changes after the head was defined: the deferred result must use the OLD values
+        CM dX2(X);
+        CM G2 = head(dX2, oneK1, dY);
+        dX2 += dX2;
+        check(max_abs_diff(G2.to_host(), want) < 1e-7f, "a source modified after the deferral does not leak into the head");
+    }
+
     // (15) random programs over a pool of matrices: every aliasing pattern the API allows (source == destination, T()
     //      views of the destination, copies taken before a source changes, rvalue chains, products feeding chains,
     //      broadcast idioms, refills).  The dump of this section must be bit-identical between the deferred and the

@@ -59,8 +59,8 @@ static int run_rank(int world, int rank, SharedPage* page) {
         unsigned cs = 0;
         for (size_t i = 0; i < m * n; i++) { unsigned u; std::memcpy(&u, gh.data() + i, 4); cs = cs * 31u + u; }
         page->checksum[rank] = cs;
-        std::printf("rank %d/%d: sharded dot + chain %zux%zux%zu, columns [%zu, %zu): rel err vs single-GPU product %.2e\n", rank, world, m, n, k,
-                    j0, j1, err);
+        std::printf("rank %d/%d: sharded dot + chain %zux%zux%zu, columns [%zu, %zu): rel err vs single-GPU product %.2e, checksum %08x\n", rank,
+                    world, m, n, k, j0, j1, err, cs);
         bad += !(err < 1e-6f);
         // ---- 2. column sums over row-sharded data
         const size_t rows = 3000, cols = 517;
@@ -87,6 +87,7 @@ static int run_rank(int world, int rank, SharedPage* page) {
 }
 
 int main(int argc, char** argv) {
+    setvbuf(stdout, nullptr, _IOLBF, 0);
     const int world = argc > 1 ? std::atoi(argv[1]) : 2;
     if (world < 1 || world > 8) { std::fprintf(stderr, "world must be 1..8\n"); return 2; }
     auto* page = static_cast<SharedPage*>(mmap(nullptr, sizeof(SharedPage), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0));
@@ -95,14 +96,24 @@ int main(int argc, char** argv) {
     std::vector<pid_t> kids;
     for (int r = 0; r < world; r++) {
         pid_t p = fork();
-        if (p == 0) _exit(run_rank(world, r, page) ? 1 : 0);
+        if (p == 0) {
+            const int rc = run_rank(world, r, page);
+            std::fflush(stdout);   // _exit skips the stdio flush
+            std::fflush(stderr);
+            _exit(rc ? 1 : 0);
+        }
         kids.push_back(p);
     }
     int failed = 0;
-    for (pid_t p : kids) {
+    for (size_t r = 0; r < kids.size(); r++) {
         int st = 0;
-        waitpid(p, &st, 0);
-        failed += !(WIFEXITED(st) && WEXITSTATUS(st) == 0);
+        waitpid(kids[r], &st, 0);
+        const bool ok = WIFEXITED(st) && WEXITSTATUS(st) == 0;
+        if (!ok) {
+            if (WIFSIGNALED(st)) std::printf("rank %zu: killed by signal %d\n", r, WTERMSIG(st));
+            else std::printf("rank %zu: exit status %d\n", r, WEXITSTATUS(st));
+        }
+        failed += !ok;
     }
     bool same = true;
     for (int r = 1; r < world; r++) same &= page->checksum[r] == page->checksum[0];

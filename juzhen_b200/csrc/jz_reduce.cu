@@ -987,6 +987,12 @@ int jz_softmax_ce_grad(float* out, const float* x, const float* y, size_t rows, 
     return softmax_impl(out, x, y, rows, cols, rows, 1, rnb, as_stream(stream));
 }
 
+int jz_softmax_ce_grad_scaled(float* out, const float* x, const float* y, size_t rows, size_t cols, float rnb,
+                              jz_stream_t stream) {
+    JZ_INIT_OR_RETURN();
+    return softmax_impl(out, x, y, rows, cols, rows, 1, rnb, as_stream(stream));
+}
+
 int jz_nrm2(const float* x, size_t n, float* result_host, jz_stream_t stream) {
     JZ_INIT_OR_RETURN();
     if (!result_host) return fail(JZ_ERR_ARG, "jz_nrm2: null result pointer");
