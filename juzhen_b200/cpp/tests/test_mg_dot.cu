@@ -77,7 +77,7 @@ static int run_rank(int world, int rank, SharedPage* page) {
             for (size_t j = 0; j < cols; j++)
                 for (size_t i = 0; i < rows; i++) ref[j] += Xr.elem(i, j);
         }
-        for (size_t j = 0; j < cols; j++) worst = std::max(worst, std::fabs(th.elem(j, 0) - ref[j]));
+        for (size_t j = 0; j < cols; j++) worst = std::max(worst, std::fabs(th.elem(0, j) - ref[j]));   // sum(X, 0) is a logical 1 x cols row
         std::printf("rank %d/%d: row-sharded column sums + allreduce: max abs err %.2e\n", rank, world, worst);
         bad += !(worst < 1e-5 * std::sqrt(double(rows * world)) * 4);
         comm.barrier();
