@@ -57,12 +57,15 @@ for stage in "$@"; do
           python scripts/config1_probe.py > gpurun_out/${TAG}_ncu_config1.log 2>&1
       tail -3 gpurun_out/${TAG}_ncu_config1.log
       ncu -i gpurun_out/${TAG}_config1.ncu-rep --page source --csv > gpurun_out/${TAG}_config1_source.csv 2>/dev/null
-      ncu -i gpurun_out/${TAG}_config1.ncu-rep --page raw --csv > gpurun_out/${TAG}_config1_raw.csv 2>/dev/null; wc -c gpurun_out/${TAG}_config1_*.csv ;;
+      ncu -i gpurun_out/${TAG}_config1.ncu-rep --page raw --csv > gpurun_out/${TAG}_config1_raw.csv 2>/dev/null; wc -c gpurun_out/${TAG}_config1_*.csv
+      [ $(stat -c %s gpurun_out/${TAG}_config1.ncu-rep) -gt 20000000 ] && rm -f gpurun_out/${TAG}_config1.ncu-rep ;;
     ncu_gemm)
-      timeout -k 5 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 6 -c 12 -o gpurun_out/${TAG}_gemm -f \
-          python scripts/gemm_sweep.py ${arg:-1024 4096} > gpurun_out/${TAG}_ncu_gemm.log 2>&1
+      timeout -k 5 900 ncu --set full --clock-control none -k regex:gemm_tcgen05 -c 12 -o gpurun_out/${TAG}_gemm -f \
+          python scripts/ncu_gemm_probe.py ${arg//,/ } > gpurun_out/${TAG}_ncu_gemm.log 2>&1
       tail -3 gpurun_out/${TAG}_ncu_gemm.log
-      ncu -i gpurun_out/${TAG}_gemm.ncu-rep --page raw --csv > gpurun_out/${TAG}_gemm_raw.csv 2>/dev/null; wc -c gpurun_out/${TAG}_gemm_raw.csv ;;
+      ncu -i gpurun_out/${TAG}_gemm.ncu-rep --page raw --csv > gpurun_out/${TAG}_gemm_raw.csv 2>/dev/null; wc -c gpurun_out/${TAG}_gemm_raw.csv
+      # gpurun copies back at most 64 MiB: keep the report only when it is small
+      [ $(stat -c %s gpurun_out/${TAG}_gemm.ncu-rep) -gt 20000000 ] && rm -f gpurun_out/${TAG}_gemm.ncu-rep ;;
     ncu_launches)
       timeout -k 5 1500 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/${TAG}_ncu_launches.csv \
           python bench.py --steps 2 --warmup 1 --no-cpu --no-mnist > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
