@@ -334,6 +334,15 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
             if (rc == JZ_OK) rc = ws_alloc(&ws, size_t(split_tiles) * size_t(args.splits) * size_t(cg * TILE_M * tn) * sizeof(float), s);
             if (rc == JZ_OK) args.ws = static_cast<float*>(ws);
         }
+        // single-pass TF32 with more units than SM pairs: the persistent kernel (epilogue of unit i under the mainloop of
+        // unit i + 1).  JZ_GEMM_PERSIST=0 disables it, =1 forces it whenever the shape allows.
+        static const int f_persist = [] {
+            const char* e = std::getenv("JZ_GEMM_PERSIST");
+            return e && *e ? std::atoi(e) : -1;
+        }();
+        const unsigned n_units = args.full_tiles + split_tiles * unsigned(args.splits);
+        const bool persist_ok = !split3x && cg == 2 && tn == 256 && batch == 1;
+        const bool persist = persist_ok && (f_persist == 1 || (f_persist != 0 && n_units > unsigned(ctx().sm_count) / 2));
         if (rc == JZ_OK) {
             for (unsigned b0 = 0; b0 < batch && rc == JZ_OK; b0 += 65535u) {   // grid.z limit
                 const unsigned nb = batch - b0 < 65535u ? batch - b0 : 65535u;
@@ -342,6 +351,7 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
                 bb.ptr += size_t(b0) * b.batch_stride;
                 GemmArgs ar = args;
                 ar.C += size_t(b0) * strideC;
+                if (persist) { rc = launch_tc_tf32_persistent(ab, bb, ar, s); continue; }
                 if (split3x) rc = cg == 2 ? launch_tc_cg<MODE_XFORM, 2>(tn, ab, bb, ar, nb, s) : launch_tc_cg<MODE_XFORM, 1>(tn, ab, bb, ar, nb, s);
                 else rc = cg == 2 ? launch_tc_cg<MODE_TF32, 2>(tn, ab, bb, ar, nb, s) : launch_tc_cg<MODE_TF32, 1>(tn, ab, bb, ar, nb, s);
             }

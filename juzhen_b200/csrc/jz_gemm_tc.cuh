@@ -95,6 +95,8 @@ struct Operand {
 // jz_gemm_tc_*.cu: one definition per MODE x CG
 template <int MODE, int CG>
 int launch_tc_cg(int tn, const Operand& a, const Operand& b, const GemmArgs& args, unsigned batch, cudaStream_t s);
+// jz_gemm_tc_tf32_persist.cu: the persistent single-pass TF32 kernel (CTA pairs, 256 x 256 tiles, single products)
+int launch_tc_tf32_persistent(const Operand& a, const Operand& b, const GemmArgs& args, cudaStream_t s);
 
 #ifdef JZ_GEMM_TC_IMPL   // ------------------------------------------------------------------ kernel side
 
@@ -701,6 +703,348 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 1) tmem_dealloc<CG>(tmem_base, 2 * TILE_N);
 }
 
+// ======================================================================= persistent TF32 kernel
+// Single-pass TF32, CTA pair per 256 x 256 tile, PERSISTENT: a pair walks the units pair, pair + P, pair + 2P ... (P pairs
+// resident) and the accumulator of unit i + 1 fills the other TMEM half while the epilogue warps drain, finish and
+// store unit i.  ncu on the one-tile-per-pair kernel shows why: at 4096^3 the tensor pipe is active only 69 % of the
+// time in TF32 mode, the rest is the per-tile prologue (TMEM allocation, barrier init, first TMA round trip) and the
+// epilogue (accumulator drain + 256 KB of stores), ~12 us per wave that nothing hides (profiles/r02c_ncu_gemm_summary.txt).
+// Here the prologue is paid once per launch and the epilogue runs under the next unit's mainloop.
+//   * the whole k range of a unit is chained in TMEM (no register-level promotion: TF32 mode is input-rounding
+//     dominated, 7e-4; the chain's truncation adds < 1.2e-4 at k = 16384);
+//   * epilogue: 4 x tcgen05.ld (128 columns per warp) into registers, TMEM half released at once, then alpha / beta /
+//     bias / program / stores exactly as in gemm_tcgen05_kernel (program through a per-warp scratch that this kernel
+//     owns, the operand stages being busy with the next unit);
+//   * units are the same list as in the one-shot kernel (whole tiles, then k-splits of the last partial wave, which
+//     meet through workspace and a ticket); pairs stay in step because every pair runs at the tensor pipe's rate, so
+//     the tiles of a "wave" still share their A / B panels in L2.
+constexpr int P_STAGES = 6;                                   // 6 x 32 KB operand stages
+constexpr int P_STAGE_BYTES = A_BYTES + (256 / 2) * BK * 4;   // 32 KB: 128 rows of A + 128 rows of B per CTA
+constexpr int P_SCRATCH_BYTES = NUM_EPI_WARPS * 4096;         // per-warp 32 x 32 scratch for the elementwise program
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES + 1024 + 256;
+
+struct UnitInfo {
+    int m0, n0, nb0, kb0, num_kb, split;
+    unsigned split_tile;
+};
+__device__ __forceinline__ UnitInfo decode_unit(const GemmArgs& args, unsigned unit, uint32_t rank, int tile_n) {
+    UnitInfo u;
+    const int num_kb_total = int((args.k + BK - 1) / BK);
+    unsigned tile = unit;
+    u.kb0 = 0; u.num_kb = num_kb_total; u.split = -1; u.split_tile = 0;
+    if (unit >= args.full_tiles) {
+        const unsigned r = unit - args.full_tiles;
+        u.split_tile = r / unsigned(args.splits);
+        u.split = int(r % unsigned(args.splits));
+        tile = args.full_tiles + u.split_tile;
+        u.kb0 = u.split * args.kb_per_split;
+        u.num_kb = num_kb_total - u.kb0 < args.kb_per_split ? num_kb_total - u.kb0 : args.kb_per_split;
+    }
+    constexpr unsigned GROUP = 8;
+    const unsigned per_group = GROUP * args.tiles_n;
+    const unsigned group_id = tile / per_group;
+    const unsigned first_m = group_id * GROUP;
+    const unsigned group_m = args.tiles_m - first_m < GROUP ? args.tiles_m - first_m : GROUP;
+    const unsigned tm = first_m + (tile % per_group) % group_m;
+    const unsigned tn = (tile % per_group) / group_m;
+    u.m0 = int(tm) * (2 * TILE_M) + int(rank) * TILE_M;
+    u.n0 = int(tn) * tile_n;
+    u.nb0 = u.n0 + int(rank) * (tile_n / 2);
+    return u;
+}
+
+template <bool AMN, bool BMN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args,
+                            const unsigned total_units) {
+    constexpr int CG = 2, TILE_N = 256, HALF_N = 128, STAGES = P_STAGES, STAGE_BYTES = P_STAGE_BYTES;
+    constexpr int B_ROWS = 128;
+    constexpr uint32_t IDESC = make_idesc_tf32(256, TILE_N, AMN, BMN);
+    constexpr uint32_t KA = kstep_bytes<AMN>(), KB = kstep_bytes<BMN>();
+    constexpr int TILE_ELEMS = TILE_M * TILE_N;
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ ChainParams s_chain;
+    __shared__ float* s_peers[JZ_MAX_PEERS];
+    stage_chain(&s_chain, args.chain, threadIdx.x);
+    if (threadIdx.x == 32) {
+#pragma unroll
+        for (int q = 0; q < JZ_MAX_PEERS; q++) s_peers[q] = args.peers[q];
+    }
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES + P_SCRATCH_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+    auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + P_SCRATCH_BYTES + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const unsigned pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && elect_one()) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        if (elect_one()) {
+            for (int s = 0; s < STAGES; s++) {
+                mbar_init(full_bar(s), 1);
+                mbar_init(empty_bar(s), 1);
+            }
+            for (int b = 0; b < 2; b++) {
+                mbar_init(tmem_full_bar(b), 1);
+                mbar_init(tmem_empty_bar(b), NUM_EPI_WARPS * CG);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<CG>(tmem_slot, 2 * TILE_N);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ===================== TMA producer: one continuous k-block stream over this pair's units =====================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (unsigned unit = pair; unit < total_units; unit += num_pairs) {
+                const UnitInfo u = decode_unit(args, unit, rank, TILE_N);
+                for (int kb = 0; kb < u.num_kb; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (leader) mbar_arrive_expect_tx(full_bar(stage), uint32_t(STAGE_BYTES) * CG);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const int kc = (u.kb0 + kb) * BK;
+                    tma_load_tile<AMN, TILE_M, true>(sa, &tmA, full_bar(stage), kc, u.m0, 0);
+                    tma_load_tile<BMN, B_ROWS, true>(sa + A_BYTES, &tmB, full_bar(stage), kc, u.nb0, 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA): unit i accumulates in TMEM half i & 1 =====================
+        if (leader) {
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (unsigned unit = pair; unit < total_units; unit += num_pairs, it++) {
+                const UnitInfo u = decode_unit(args, unit, rank, TILE_N);
+                const uint32_t buf = it & 1u;
+                mbar_wait(tmem_empty_bar(buf), ((it >> 1) & 1u) ^ 1u);   // the epilogue warps have read this half out
+                tc_fence_after();
+                for (int kb = 0; kb < u.num_kb; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t d = tmem_base + buf * TILE_N;
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < BK / UMMA_K; ks++)
+                            umma_tf32<CG>(d, make_smem_desc<AMN>(sa + ks * KA), make_smem_desc<BMN>(sa + A_BYTES + ks * KB), IDESC,
+                                          (kb | ks) ? 1u : 0u);
+                        umma_commit<CG>(empty_bar(stage));
+                        if (kb == u.num_kb - 1) umma_commit<CG>(tmem_full_bar(buf));
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps: drain a finished unit while the next one is being multiplied =====================
+        const int e = warp - FIRST_EPI_WARP;
+        const int quarter = warp & 3;
+        const int half = e >> 2;
+        const int lane = threadIdx.x & 31;
+        const int te = threadIdx.x - 32 * FIRST_EPI_WARP;
+        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * HALF_N);
+        const uint32_t empty0 = tmem_empty_bar(0) & 0xFEFFFFFFu, empty1 = tmem_empty_bar(1) & 0xFEFFFFFFu;
+        float* const sw = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES) + e * 1024;
+        const size_t ldc = args.ldc;
+        float* const Cb = args.C;
+        uint32_t it = 0;
+        for (unsigned unit = pair; unit < total_units; unit += num_pairs, it++) {
+            const UnitInfo u = decode_unit(args, unit, rank, TILE_N);
+            const uint32_t buf = it & 1u;
+            mbar_wait(tmem_full_bar(buf), (it >> 1) & 1u);
+            tc_fence_after();
+            float acc[HALF_N];
+#pragma unroll
+            for (int p = 0; p < HALF_N / 32; p++) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(lane_addr + buf * TILE_N + p * 32, r);
+#pragma unroll
+                for (int c = 0; c < 32; c++) acc[p * 32 + c] = __uint_as_float(r[c]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(buf ? empty1 : empty0);   // this TMEM half may be overwritten now
+            if (u.split < 0) {
+                const size_t row = size_t(u.m0) + quarter * 32 + lane;
+                const bool row_ok = row < args.m;
+                const size_t ncol0 = size_t(u.n0) + half * HALF_N;
+#pragma unroll
+                for (int p = 0; p < HALF_N / 32; p++) {
+                    const size_t colp = ncol0 + p * 32;
+                    if (colp < args.n) {  // warp-uniform
+                        const int ncols = args.n - colp < 32 ? int(args.n - colp) : 32;
+                        float v[32];
+#pragma unroll
+                        for (int c = 0; c < 32; c++) v[c] = args.alpha * acc[p * 32 + c];
+                        if (args.beta != 0.0f && row_ok) {
+                            const float* src = Cb + row + colp * ldc;
+#pragma unroll
+                            for (int c = 0; c < 32; c++) {
+                                if (c < ncols) v[c] += args.beta * *src;
+                                src += ldc;
+                            }
+                        }
+                        if (s_chain.bias) {
+                            const float br = s_chain.bias_dim == 1 ? s_chain.bias[row_ok ? row : 0] : 0.0f;
+#pragma unroll
+                            for (int c = 0; c < 32; c++) {
+                                const float bv = s_chain.bias_dim == 1 ? br : s_chain.bias[c < ncols ? colp + c : colp];
+                                v[c] = __fadd_rn(__fmul_rn(s_chain.bias_s1, v[c]), __fmul_rn(s_chain.bias_s2, bv));
+                            }
+                        }
+                        if (s_chain.n) {
+                            __syncwarp();
+#pragma unroll
+                            for (int c = 0; c < 32; c++) sw[c * 32 + lane] = v[c];
+                            __syncwarp();
+#pragma unroll 1
+                            for (int c0 = 0; c0 < ncols; c0 += 8) {
+                                float w[8];
+#pragma unroll
+                                for (int q = 0; q < 8; q++) w[q] = sw[(c0 + q) * 32 + lane];
+                                apply_chain<8>(w, s_chain);
+                                if (row_ok) {
+                                    if (args.mc) {
+#pragma unroll
+                                        for (int q = 0; q < 8; q++)
+                                            if (c0 + q < ncols) multimem_st(args.mc + row + (colp + c0 + q) * ldc, w[q]);
+                                    } else {
+                                        for (int d = 0; d <= args.n_peers; d++) {
+                                            float* dst = (d == 0 ? Cb : s_peers[d - 1]) + row + (colp + c0) * ldc;
+#pragma unroll
+                                            for (int q = 0; q < 8; q++) {
+                                                if (c0 + q < ncols) *dst = w[q];
+                                                dst += ldc;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                            continue;
+                        }
+                        if (row_ok) {
+                            if (args.mc) {
+                                float* dst = args.mc + row + colp * ldc;
+#pragma unroll
+                                for (int c = 0; c < 32; c++) {
+                                    if (c < ncols) multimem_st(dst, v[c]);
+                                    dst += ldc;
+                                }
+                            } else {
+                                for (int d = 0; d <= args.n_peers; d++) {
+                                    float* dst = (d == 0 ? Cb : s_peers[d - 1]) + row + colp * ldc;
+#pragma unroll
+                                    for (int c = 0; c < 32; c++) {
+                                        if (c < ncols) *dst = v[c];
+                                        dst += ldc;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                // ---- k-split unit (same protocol as gemm_tcgen05_kernel): park the partial, ticket, finish a column slice
+                const int S = args.splits;
+                const unsigned want = unsigned(S) * CG;
+                float* const ws_tile = args.ws + size_t(u.split_tile) * size_t(S) * (CG * TILE_ELEMS);
+                {
+                    float* dst = ws_tile + (size_t(u.split) * CG + rank) * TILE_ELEMS + size_t(half * HALF_N) * TILE_M + quarter * 32 + lane;
+#pragma unroll
+                    for (int c = 0; c < HALF_N; c++) __stcg(dst + c * TILE_M, acc[c]);
+                }
+                __threadfence();
+                epi_bar_sync();
+                unsigned* const tk = args.tickets + u.split_tile;
+                if (te == 0) {
+                    atomicAdd(tk, 1u);
+                    while (ld_acquire_gpu(tk) < want) __nanosleep(20);
+                }
+                epi_bar_sync();
+                __threadfence();
+                const int c_begin = u.split * TILE_N / S, c_end = (u.split + 1) * TILE_N / S;
+                const int r4 = (te & 31) * 4, cl = te >> 5;
+                const size_t row0 = size_t(u.m0) + r4;
+                const bool vec_ok = (ldc & 3) == 0 && aligned16(Cb) && row0 + 3 < args.m;
+                const float* const src0 = ws_tile + size_t(rank) * TILE_ELEMS + r4;
+                const size_t sstride = size_t(CG) * TILE_ELEMS;
+                for (int c = c_begin + cl; c < c_end; c += 8) {
+                    float4 a4 = __ldcg(reinterpret_cast<const float4*>(src0 + size_t(c) * TILE_M));
+#pragma unroll 4
+                    for (int s = 1; s < S; s++) {
+                        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src0 + size_t(s) * sstride + size_t(c) * TILE_M));
+                        a4.x = __fadd_rn(a4.x, t4.x); a4.y = __fadd_rn(a4.y, t4.y); a4.z = __fadd_rn(a4.z, t4.z); a4.w = __fadd_rn(a4.w, t4.w);
+                    }
+                    const size_t col = size_t(u.n0) + c;
+                    if (col >= args.n || row0 >= args.m) continue;
+                    float v[4] = {args.alpha * a4.x, args.alpha * a4.y, args.alpha * a4.z, args.alpha * a4.w};
+                    float* const dstc = Cb + row0 + col * ldc;
+                    if (args.beta != 0.0f) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (row0 + q < args.m) v[q] += args.beta * dstc[q];
+                    }
+                    if (s_chain.bias) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) v[q] = apply_bias(v[q], s_chain, row0 + q < args.m ? row0 + q : row0, col);
+                    }
+                    if (s_chain.n) apply_chain<4>(v, s_chain);
+                    if (args.mc) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (row0 + q < args.m) multimem_st(args.mc + row0 + q + col * ldc, v[q]);
+                    } else {
+                        for (int d = 0; d <= args.n_peers; d++) {
+                            float* const dd = (d == 0 ? Cb : s_peers[d - 1]) + row0 + col * ldc;
+                            if (vec_ok) {
+                                *reinterpret_cast<float4*>(dd) = make_float4(v[0], v[1], v[2], v[3]);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; q++)
+                                    if (row0 + q < args.m) dd[q] = v[q];
+                            }
+                        }
+                    }
+                }
+                epi_bar_sync();
+                if (te == 0) {
+                    unsigned* const dn = args.tickets + (kTicketSlots / 2) + u.split_tile;
+                    if (atomicAdd(dn, 1u) == want - 1) {
+                        *tk = 0;
+                        *dn = 0;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc<CG>(tmem_base, 2 * TILE_N);
+}
+
 // ----------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -786,6 +1130,47 @@ static int launch_tc(const Operand& a, const Operand& b, const GemmArgs& args, u
     ctx().launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return cuda_fail(e, "gemm_tcgen05_kernel launch");
     return JZ_OK;
+}
+
+// persistent TF32 kernel: grid = min(units, resident pairs) CTA pairs
+template <bool AMN, bool BMN>
+static int launch_tf32_persistent(const Operand& a, const Operand& b, const GemmArgs& args, cudaStream_t s) {
+    alignas(64) CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_map(&ma, a, args.m, args.k, TILE_M, 1)) != JZ_OK) return rc;
+    if ((rc = make_map(&mb, b, args.n, args.k, 128, 1)) != JZ_OK) return rc;
+    auto kern = gemm_tf32_persistent_kernel<AMN, BMN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        JZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+        attr_done = true;
+    }
+    const unsigned tiles = args.tiles_m * args.tiles_n;
+    const unsigned units = args.full_tiles + (tiles - args.full_tiles) * unsigned(args.splits);
+    const unsigned pairs = unsigned(ctx().sm_count) / 2;
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((units < pairs ? units : pairs) * 2, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = P_SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, args, units);
+    ctx().launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return cuda_fail(e, "gemm_tf32_persistent_kernel launch");
+    return JZ_OK;
+}
+static int launch_tf32_persistent_major(const Operand& a, const Operand& b, const GemmArgs& args, cudaStream_t s) {
+    if (a.mn) return b.mn ? launch_tf32_persistent<true, true>(a, b, args, s) : launch_tf32_persistent<true, false>(a, b, args, s);
+    return b.mn ? launch_tf32_persistent<false, true>(a, b, args, s) : launch_tf32_persistent<false, false>(a, b, args, s);
 }
 
 // operand majors are compile-time (they select TMA box shapes and descriptor layouts)
