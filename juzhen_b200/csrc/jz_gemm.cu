@@ -342,7 +342,11 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         }();
         const unsigned n_units = args.full_tiles + split_tiles * unsigned(args.splits);
         const bool persist_ok = !split3x && cg == 2 && tn == 256 && batch == 1;
-        const bool persist = persist_ok && (f_persist == 1 || (f_persist != 0 && n_units > unsigned(ctx().sm_count) / 2));
+        // ... while the operands of a wave of tiles fit in L2 (up to 8192^2 x 2): beyond that the tiles of a wave must read
+        // their shared A / B panels at the same moment, and persistent pairs drift apart over a long launch (measured at
+        // 16384^3: 602 -> 545 TFLOP/s, A.T*B 552 -> 432; at 4096^3 689 -> 729, profiles/r02d_gemm_tf32_persistent_ab.log)
+        const bool fits_l2_wave = (double(m) + double(n)) * double(k) * 4.0 <= 540e6;
+        const bool persist = persist_ok && (f_persist == 1 || (f_persist != 0 && fits_l2_wave && n_units > unsigned(ctx().sm_count) / 2));
         if (rc == JZ_OK) {
             for (unsigned b0 = 0; b0 < batch && rc == JZ_OK; b0 += 65535u) {   // grid.z limit
                 const unsigned nb = batch - b0 < 65535u ? batch - b0 : 65535u;
