@@ -399,10 +399,10 @@ def run_sharded_colsum(jz, L, sw, world, stream, timed, pk):
 
 def run_config1(jz, L, stream, timed, pk, no_cpu=False):
     """BASELINE configs[0]: 4096 x 4096 fp32 A*B then log(exp(A*B/4096)+1)/5 (examples/demo_gemm.cu:41-95 style; the
-    1/4096 keeps exp finite).  Three spellings on the GPU -- the chain fused into the GEMM
-    epilogue (1 launch), GEMM + one fused elementwise pass (2 launches), GEMM + the five separate maps an
-    lvalue-by-lvalue operator chain issues (6 launches) -- and the reference's own CPU result (Matrix<float>, OpenBLAS)
-    on the same inputs as the comparator and the CPU bar."""
+    1/4096 keeps exp finite).  Three spellings on the GPU -- jz_gemm_chain (what the C++ shell
+    emits for the deferred expression), GEMM + one fused elementwise pass (2 launches), GEMM + the five separate maps
+    an lvalue-by-lvalue operator chain issues (6 launches) -- and the reference's own CPU result (Matrix<float>,
+    OpenBLAS) on the same inputs as the comparator and the CPU bar."""
     import numpy as np
     n = 4096
     rng = np.random.default_rng(41)
@@ -435,7 +435,10 @@ def run_config1(jz, L, stream, timed, pk, no_cpu=False):
 
     out = {"workload": "BASELINE configs[0]: 4096^2 fp32 A*B then log(exp(A*B/4096)+1)/5, 3xTF32 (fp32 accuracy)"}
     peak = pk["bf16_tflops"] / 2 / 3
-    for name, fn in (("fused_epilogue_1_launch", fused), ("gemm_plus_fused_chain_2_launches", gemm_then_chain),
+    # jz_gemm_chain decides by itself: a program with transcendental steps on an output this large runs as the product
+    # plus ONE streaming pass (the one-shot kernel cannot hide a 45-instruction-per-element epilogue), lighter programs
+    # and multi-GPU gathers stay in the epilogue; bit-identical either way
+    for name, fn in (("jz_gemm_chain", fused), ("gemm_plus_jz_chain_2_launches", gemm_then_chain),
                      ("gemm_plus_5_maps_6_launches", gemm_then_maps)):
         ms, _ = timed(fn, 10, 3)
         tf = 2.0 * n ** 3 / (ms * 1e-3) / 1e12

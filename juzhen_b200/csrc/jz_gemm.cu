@@ -424,6 +424,26 @@ static int gemm_local(int ta, int tb, size_t m, size_t n, size_t k, float alpha,
     if (want_tc && big_enough && fits_i32 && !force_simt) {
         const bool split3x = mode == JZ_GEMM_3XTF32;
         *fused_done = true;
+        // A program with transcendental steps costs ~45 instructions per element.  In the one-shot kernel the epilogue of
+        // a tile is not hidden under another tile's mainloop, so on a large output that work sits in the tail of every
+        // wave with only the epilogue warps busy (4096^2, log(exp(x/n)+1)/5: +60 us fused against +35 us for a separate
+        // streaming pass at full HBM rate, profiles/r02e_bench.json config1).  Such programs are therefore run as a second,
+        // streaming pass over C -- same steps, same roundings, bit-identical (fused_equals_separate_bitwise) -- unless the
+        // epilogue also carries the gather to other GPUs, or the persistent TF32 kernel (overlapped epilogue) takes the product.
+        static const bool keep_fused = std::getenv("JZ_GEMM_KEEP_FUSED") != nullptr;
+        bool heavy = false;
+        for (int i = 0; i < chain.n; i++) heavy |= chain.kind[i] == JZ_EXP || chain.kind[i] == JZ_LOG || chain.kind[i] == JZ_TANH || chain.kind[i] == JZ_DTANH;
+        const bool persistent_tf32 = !split3x && m > 128 && n > 128 && (double(m) + double(n)) * double(k) * 4.0 <= 540e6 &&
+                                     ceil_div(m, size_t(256)) * ceil_div(n, size_t(256)) > size_t(ctx().sm_count) / 2;
+        if (heavy && !keep_fused && !persistent_tf32 && ldc == m && double(m) * double(n) >= double(1 << 22) && !x.n_peers && !x.mc) {
+            ChainParams head = chain;
+            head.n = 0;   // alpha / beta / bias stay in the product
+            int rc = tc::gemm_tc(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, split3x, head, nullptr, 0, nullptr, 1, 0, 0, 0, s);
+            if (rc != JZ_OK) return rc;
+            jz_step steps[JZ_MAX_CHAIN];
+            for (int i = 0; i < chain.n; i++) steps[i] = jz_step{chain.kind[i], chain.s1[i], chain.a[i]};
+            return jz_chain(C, C, m * n, steps, chain.n, reinterpret_cast<jz_stream_t>(s));
+        }
         return tc::gemm_tc(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, split3x, chain, x.peers, x.n_peers, x.mc, 1, 0, 0, 0, s);
     }
     if (gemm_small_wants(m, n, k))   // latency-bound shapes: the warp-per-tile fp32 kernel (jz_gemm_small.cu)

@@ -715,9 +715,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   * epilogue: 4 x tcgen05.ld (128 columns per warp) into registers, TMEM half released at once, then alpha / beta /
 //     bias / program / stores exactly as in gemm_tcgen05_kernel (program through a per-warp scratch that this kernel
 //     owns, the operand stages being busy with the next unit);
-//   * units are the same list as in the one-shot kernel (whole tiles, then k-splits of the last partial wave, which
-//     meet through workspace and a ticket); pairs stay in step because every pair runs at the tensor pipe's rate, so
-//     the tiles of a "wave" still share their A / B panels in L2.
+//   * units are the same list as in the one-shot kernel (whole tiles, then k-splits of the last partial wave); the
+//     units of a split tile meet through workspace and a ticket WITHOUT waiting (the last one to arrive finishes the
+//     tile); pairs stay in step because every pair runs at the tensor pipe's rate, so the tiles of a "wave" still
+//     share their A / B panels in L2.
 constexpr int P_STAGES = 6;                                   // 6 x 32 KB operand stages
 constexpr int P_STAGE_BYTES = A_BYTES + (256 / 2) * BK * 4;   // 32 KB: 128 rows of A + 128 rows of B per CTA
 constexpr int P_SCRATCH_BYTES = NUM_EPI_WARPS * 4096;         // per-warp 32 x 32 scratch for the elementwise program
@@ -766,6 +767,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     extern __shared__ uint8_t smem_raw[];
     __shared__ ChainParams s_chain;
     __shared__ float* s_peers[JZ_MAX_PEERS];
+    __shared__ bool s_last;   // this CTA was the last of a split tile's units to arrive
     stage_chain(&s_chain, args.chain, threadIdx.x);
     if (threadIdx.x == 32) {
 #pragma unroll
@@ -965,9 +967,12 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                     }
                 }
             } else {
-                // ---- k-split unit (same protocol as gemm_tcgen05_kernel): park the partial, ticket, finish a column slice
+                // ---- k-split unit: park the partial and take a ticket; the LAST of the S units of this tile (per CTA rank)
+                // to arrive adds the S partials in split order and finishes the tile's rows of its rank.  Nobody waits:
+                // a persistent pair owns units that may not be resident yet when another kernel shares the GPU, so
+                // the waiting protocol of the one-shot kernel could stall here; the longer fix-up of the last arriver
+                // runs under the next unit's mainloop like any other epilogue.
                 const int S = args.splits;
-                const unsigned want = unsigned(S) * CG;
                 float* const ws_tile = args.ws + size_t(u.split_tile) * size_t(S) * (CG * TILE_ELEMS);
                 {
                     float* dst = ws_tile + (size_t(u.split) * CG + rank) * TILE_ELEMS + size_t(half * HALF_N) * TILE_M + quarter * 32 + lane;
@@ -976,65 +981,70 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                 }
                 __threadfence();
                 epi_bar_sync();
-                unsigned* const tk = args.tickets + u.split_tile;
-                if (te == 0) {
-                    atomicAdd(tk, 1u);
-                    while (ld_acquire_gpu(tk) < want) __nanosleep(20);
-                }
+                unsigned* const tk = args.tickets + u.split_tile * CG + rank;
+                if (te == 0) s_last = atomicAdd(tk, 1u) == unsigned(S) - 1u;
                 epi_bar_sync();
-                __threadfence();
-                const int c_begin = u.split * TILE_N / S, c_end = (u.split + 1) * TILE_N / S;
-                const int r4 = (te & 31) * 4, cl = te >> 5;
-                const size_t row0 = size_t(u.m0) + r4;
-                const bool vec_ok = (ldc & 3) == 0 && aligned16(Cb) && row0 + 3 < args.m;
-                const float* const src0 = ws_tile + size_t(rank) * TILE_ELEMS + r4;
-                const size_t sstride = size_t(CG) * TILE_ELEMS;
-                for (int c = c_begin + cl; c < c_end; c += 8) {
-                    float4 a4 = __ldcg(reinterpret_cast<const float4*>(src0 + size_t(c) * TILE_M));
+                if (s_last) {
+                    __threadfence();
+                    const int r4 = (te & 31) * 4, cl = te >> 5;
+                    const size_t row0 = size_t(u.m0) + r4;
+                    const bool vec_ok = (ldc & 3) == 0 && aligned16(Cb) && row0 + 3 < args.m;
+                    const float* const src0 = ws_tile + size_t(rank) * TILE_ELEMS + r4;
+                    const size_t sstride = size_t(CG) * TILE_ELEMS;
+                    constexpr int UB = 4;
+                    for (int cb = cl; cb < TILE_N; cb += 8 * UB) {
+                        float4 a4[UB];
+#pragma unroll
+                        for (int q = 0; q < UB; q++) a4[q] = __ldcg(reinterpret_cast<const float4*>(src0 + size_t(cb + 8 * q) * TILE_M));
 #pragma unroll 4
-                    for (int s = 1; s < S; s++) {
-                        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src0 + size_t(s) * sstride + size_t(c) * TILE_M));
-                        a4.x = __fadd_rn(a4.x, t4.x); a4.y = __fadd_rn(a4.y, t4.y); a4.z = __fadd_rn(a4.z, t4.z); a4.w = __fadd_rn(a4.w, t4.w);
-                    }
-                    const size_t col = size_t(u.n0) + c;
-                    if (col >= args.n || row0 >= args.m) continue;
-                    float v[4] = {args.alpha * a4.x, args.alpha * a4.y, args.alpha * a4.z, args.alpha * a4.w};
-                    float* const dstc = Cb + row0 + col * ldc;
-                    if (args.beta != 0.0f) {
+                        for (int s = 1; s < S; s++) {
+                            float4 t4[UB];
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (row0 + q < args.m) v[q] += args.beta * dstc[q];
-                    }
-                    if (s_chain.bias) {
+                            for (int q = 0; q < UB; q++)
+                                t4[q] = __ldcg(reinterpret_cast<const float4*>(src0 + size_t(s) * sstride + size_t(cb + 8 * q) * TILE_M));
 #pragma unroll
-                        for (int q = 0; q < 4; q++) v[q] = apply_bias(v[q], s_chain, row0 + q < args.m ? row0 + q : row0, col);
-                    }
-                    if (s_chain.n) apply_chain<4>(v, s_chain);
-                    if (args.mc) {
+                            for (int q = 0; q < UB; q++) {
+                                a4[q].x = __fadd_rn(a4[q].x, t4[q].x); a4[q].y = __fadd_rn(a4[q].y, t4[q].y);
+                                a4[q].z = __fadd_rn(a4[q].z, t4[q].z); a4[q].w = __fadd_rn(a4[q].w, t4[q].w);
+                            }
+                        }
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (row0 + q < args.m) multimem_st(args.mc + row0 + q + col * ldc, v[q]);
-                    } else {
-                        for (int d = 0; d <= args.n_peers; d++) {
-                            float* const dd = (d == 0 ? Cb : s_peers[d - 1]) + row0 + col * ldc;
-                            if (vec_ok) {
-                                *reinterpret_cast<float4*>(dd) = make_float4(v[0], v[1], v[2], v[3]);
+                        for (int q = 0; q < UB; q++) {
+                            const size_t col = size_t(u.n0) + cb + 8 * q;
+                            if (col >= args.n || row0 >= args.m) continue;
+                            float v[4] = {args.alpha * a4[q].x, args.alpha * a4[q].y, args.alpha * a4[q].z, args.alpha * a4[q].w};
+                            float* const dstc = Cb + row0 + col * ldc;
+                            if (args.beta != 0.0f) {
+#pragma unroll
+                                for (int t = 0; t < 4; t++)
+                                    if (row0 + t < args.m) v[t] += args.beta * dstc[t];
+                            }
+                            if (s_chain.bias) {
+#pragma unroll
+                                for (int t = 0; t < 4; t++) v[t] = apply_bias(v[t], s_chain, row0 + t < args.m ? row0 + t : row0, col);
+                            }
+                            if (s_chain.n) apply_chain<4>(v, s_chain);
+                            if (args.mc) {
+#pragma unroll
+                                for (int t = 0; t < 4; t++)
+                                    if (row0 + t < args.m) multimem_st(args.mc + row0 + t + col * ldc, v[t]);
                             } else {
+                                for (int d = 0; d <= args.n_peers; d++) {
+                                    float* const dd = (d == 0 ? Cb : s_peers[d - 1]) + row0 + col * ldc;
+                                    if (vec_ok) {
+                                        *reinterpret_cast<float4*>(dd) = make_float4(v[0], v[1], v[2], v[3]);
+                                    } else {
 #pragma unroll
-                                for (int q = 0; q < 4; q++)
-                                    if (row0 + q < args.m) dd[q] = v[q];
+                                        for (int t = 0; t < 4; t++)
+                                            if (row0 + t < args.m) dd[t] = v[t];
+                                    }
+                                }
                             }
                         }
                     }
+                    if (te == 0) *tk = 0;   // ready for the next launch on this stream
                 }
-                epi_bar_sync();
-                if (te == 0) {
-                    unsigned* const dn = args.tickets + (kTicketSlots / 2) + u.split_tile;
-                    if (atomicAdd(dn, 1u) == want - 1) {
-                        *tk = 0;
-                        *dn = 0;
-                    }
-                }
+                epi_bar_sync();   // s_last is rewritten by the next split unit
             }
         }
     }
