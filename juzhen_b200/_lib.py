@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjz_b200.so")
+LIB_PATH = os.environ.get("JZ_B200_LIB") or os.path.join(_HERE, "libjz_b200.so")   # override: an instrumented build (scripts/build_prof_lib.sh)
 
 MG_HANDLE_BYTES = 128
 JZ_OK, JZ_ERR_SHAPE, JZ_ERR_CUDA, JZ_ERR_OOM, JZ_ERR_ARG, JZ_ERR_UNSUPPORTED = range(6)

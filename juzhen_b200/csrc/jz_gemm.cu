@@ -293,6 +293,13 @@ static void plan_units(GemmArgs& a, int cg, bool split3x, unsigned batch) {
     a.kb_per_split = kbs;
 }
 
+#ifdef JZ_GEMM_PROFILE
+long long* prof_buf() {
+    static long long* p = [] { void* q = nullptr; cudaMalloc(&q, 32 * sizeof(long long)); cudaMemset(q, 0, 32 * sizeof(long long)); return static_cast<long long*>(q); }();
+    return p;
+}
+#endif
+
 static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, const float* A, size_t lda,
                    const float* B, size_t ldb, float beta, float* C, size_t ldc, bool split3x, const ChainParams& chain,
                    float* const* peers, int n_peers, float* mc, unsigned batch, size_t strideA, size_t strideB,
@@ -313,8 +320,21 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         args.chain = chain;
         args.ws = nullptr;
         args.tickets = nullptr;
+#ifdef JZ_GEMM_PROFILE
+        args.prof = prof_buf();
+#endif
         int cg, tn;
         pick_tile(m, n, cg, tn);
+        // 3xTF32 on single-CTA tiles (n <= 64 or m <= 128): A's hi / lo parts go to tensor memory instead of a second
+        // shared-memory copy -- these shapes are bound by shared-memory bandwidth and by the bytes in flight per SM, not
+        // by the tensor pipe.  JZ_GEMM_TS=0 keeps the shared-memory form, =2 forces 128 x 128 TMEM-A tiles everywhere.
+        static const int f_ts = [] {
+            const char* e = std::getenv("JZ_GEMM_TS");
+            return e && *e ? std::atoi(e) : -1;
+        }();
+        bool ts = split3x && f_ts != 0 && cg == 1;
+        if (split3x && f_ts == 2) { ts = true; cg = 1; tn = n <= 64 ? 64 : 128; }
+        if (ts && tn == 256) tn = 128;
         args.tiles_m = unsigned(ceil_div(m, size_t(cg * TILE_M)));
         args.tiles_n = unsigned(ceil_div(n, size_t(tn)));
         plan_units(args, cg, split3x, batch);
@@ -356,6 +376,7 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
                 GemmArgs ar = args;
                 ar.C += size_t(b0) * strideC;
                 if (persist) { rc = launch_tc_tf32_persistent(ab, bb, ar, s); continue; }
+                if (ts) { rc = launch_tc_ts(tn, ab, bb, ar, nb, s); continue; }
                 if (split3x) rc = cg == 2 ? launch_tc_cg<MODE_XFORM, 2>(tn, ab, bb, ar, nb, s) : launch_tc_cg<MODE_XFORM, 1>(tn, ab, bb, ar, nb, s);
                 else rc = cg == 2 ? launch_tc_cg<MODE_TF32, 2>(tn, ab, bb, ar, nb, s) : launch_tc_cg<MODE_TF32, 1>(tn, ab, bb, ar, nb, s);
             }
@@ -512,10 +533,10 @@ int jz_gemm_strided_batched(int transA, int transB, size_t m, size_t n, size_t k
     cudaStream_t s = as_stream(stream);
     const double macs = double(m) * double(n) * double(k);
     static const bool no_btc = std::getenv("JZ_GEMM_NO_BATCHED_TC") != nullptr;
-    // members of at least 2^21 multiply-adds (128 x 128 x 128): below that a tile's fixed cost (prologue, TMEM allocation,
-    // epilogue) exceeds its mainloop and the small-product kernel wins (measured: seq 64, d_h 128 at 0.7x cuBLAS fp32 on
-    // the tensor path, profiles/r02_attention.log)
-    const bool tc_member = m >= 64 && n >= 64 && k >= 32 && macs >= double(1 << 21) && batch > 1 &&
+    // members of at least 64 x 64 x 32 with 2^24 multiply-adds over the whole batch.  Small members pay a tile's fixed cost
+    // (prologue, TMEM allocation, epilogue) per 0.5 M multiply-adds and still beat the fp32 small-product kernel 5x
+    // (seq 64, d_h 128, batch 2048: 0.09 ms against 0.53 ms; cuBLAS fp32 0.06 ms; profiles/r02a_attention.log, r02e_attention.log)
+    const bool tc_member = m >= 64 && n >= 64 && k >= 32 && (macs >= double(1 << 21) || macs * double(batch) >= double(1 << 24)) && batch > 1 &&
                            batch < (size_t(1) << 31) && (mode == JZ_GEMM_3XTF32 || mode == JZ_GEMM_TF32) && ctx().cc_major == 10 &&
                            m < (size_t(1) << 31) && n < (size_t(1) << 31) && k < (size_t(1) << 31) && !no_btc;
     const bool tma_ok = lda % 4 == 0 && ldb % 4 == 0 && strideA % 4 == 0 && strideB % 4 == 0 && aligned16(A) && aligned16(B);
@@ -591,3 +612,11 @@ int jz_gemm_chain_mcast(int transA, int transB, size_t m, size_t n, size_t k, fl
 int jz_gemm_last_splits(void) { return ctx().gemm_last_splits; }
 
 }  // extern "C"
+
+#ifdef JZ_GEMM_PROFILE
+// instrumented builds only (not declared in include/jz_b200.h): the cycle counters of the last tensor-core GEMM launch
+extern "C" __attribute__((visibility("default"))) int jz_debug_gemm_prof(long long* out32) {
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out32, jz::tc::prof_buf(), sizeof(long long) * 32, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -51,14 +51,23 @@ constexpr int FIRST_EPI_WARP = 2;
 constexpr int NUM_THREADS = 32 * (FIRST_EPI_WARP + NUM_EPI_WARPS);  // TMA warp + MMA warp + 8 epilogue/transform warps
 constexpr int MODE_TF32 = 0;      // single pass over the raw fp32 tiles
 constexpr int MODE_XFORM = 2;     // 3xTF32, lo computed in shared memory by the transform warps
+constexpr int MODE_XFORM_TS = 3;  // 3xTF32, A operand (hi and lo) written to TENSOR MEMORY by the transform warps (CG = 1, TN <= 128)
+constexpr int TS_SLOT_COLS = 2 * BK;   // TMEM columns of one k-block of A: 32 hi + 32 lo
 constexpr int MN_BOX_BYTES = 32 * BK * 4;  // one MN-major TMA box: 32 contiguous rows x 32 k = 4 KB
 constexpr int MAX_SPLITS = 16;
 
 template <int CG, int TN> __host__ __device__ constexpr int b_rows() { return TN / CG; }
 template <int CG, int TN> __host__ __device__ constexpr int b_bytes() { return b_rows<CG, TN>() * BK * 4; }
-template <int CG, int MODE, int TN> __host__ __device__ constexpr int stage_bytes() { return (MODE != MODE_TF32 ? 2 : 1) * (A_BYTES + b_bytes<CG, TN>()); }
+template <int CG, int MODE, int TN> __host__ __device__ constexpr int stage_bytes() {
+    if (MODE == MODE_XFORM_TS) return A_BYTES + 2 * b_bytes<CG, TN>();   // raw A, raw B, lo(B): lo(A) lives in TMEM
+    return (MODE != MODE_TF32 ? 2 : 1) * (A_BYTES + b_bytes<CG, TN>());
+}
 template <int CG, int MODE, int TN> __host__ __device__ constexpr int num_stages() {
-    constexpr int s = (227 * 1024 - 2048) / stage_bytes<CG, MODE, TN>();
+    int s = (227 * 1024 - 2048) / stage_bytes<CG, MODE, TN>();
+    if (MODE == MODE_XFORM_TS) {   // one TMEM slot per smem stage, next to the two accumulator buffers
+        const int slots = (512 - 2 * TN) / TS_SLOT_COLS;
+        if (s > slots) s = slots;
+    }
     return s > 8 ? 8 : s;
 }
 template <int CG, int MODE, int TN> __host__ __device__ constexpr int smem_bytes() {
@@ -82,6 +91,13 @@ struct GemmArgs {
     float* peers[JZ_MAX_PEERS];
     float* mc;                  // multicast (NVSwitch) image of C: when set, every element is stored by ONE multimem.st
     ChainParams chain;
+#ifdef JZ_GEMM_PROFILE
+    // instrumented build (scripts/build_prof_lib.sh): cycle counts of CTA 5, read back by jz_debug_gemm_prof
+    //   [0..2] TMA: k-blocks, total, waiting for a free stage      [3..5] MMA: total, waiting for operands, for a drained accumulator
+    //   [8 + 8 g ..] transform group g (warp e = 4 g): mainloop, waiting for TMA, transform, waiting for a chunk, drain
+    //   [24..26] epilogue: cycles, split, splits
+    long long* prof;
+#endif
 };
 
 struct Operand {
@@ -95,10 +111,13 @@ struct Operand {
 // jz_gemm_tc_*.cu: one definition per MODE x CG
 template <int MODE, int CG>
 int launch_tc_cg(int tn, const Operand& a, const Operand& b, const GemmArgs& args, unsigned batch, cudaStream_t s);
+// jz_gemm_tc_xform_ts.cu: 3xTF32 with A staged in tensor memory (CG = 1, tn = 64 | 128)
+int launch_tc_ts(int tn, const Operand& a, const Operand& b, const GemmArgs& args, unsigned batch, cudaStream_t s);
 // jz_gemm_tc_tf32_persist.cu: the persistent single-pass TF32 kernel (CTA pairs, 256 x 256 tiles, single products)
 int launch_tc_tf32_persistent(const Operand& a, const Operand& b, const GemmArgs& args, cudaStream_t s);
 
 #ifdef JZ_GEMM_TC_IMPL   // ------------------------------------------------------------------ kernel side
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -183,6 +202,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
             : "memory");
     }
 }
+// A operand from tensor memory (lane = row, one fp32 word per column = k), B from shared memory; CTA group 1 only
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc),
+        "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // tcgen05.commit: arrive on `bar` (in every CTA of the pair for CG == 2) when all prior MMAs retire
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -225,6 +252,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// 16 consecutive TMEM columns of this thread's lane (32 lanes x 32 bit per warp); caller issues tmem_st_wait()
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Shared-memory operand descriptors (sm_100 format: version 1 at bit 46).
 //   K-major tile: rows of 128 B, 128B swizzle (layout type 2), 8-row groups 1024 B apart (SBO); one UMMA_K step
@@ -276,11 +314,12 @@ __device__ __forceinline__ void multimem_st(float* mc_addr, float v) {
 // lo part of the 3xTF32 split against the hardware's own hi: kind::tf32 drops the low 13 mantissa bits of the
 // fp32 word it reads, so hi = x & 0xFFFFE000 and x - hi is exact in fp32; lo is that remainder rounded to tf32
 // (nearest, ties away: add half an ulp to the magnitude, truncate), so the tensor core reads it unchanged.
-// inf/nan keep their semantics through hi alone (lo = 0 avoids inf - inf).
+// inf/nan keep their semantics through hi alone (lo = 0 avoids inf - inf); the one corner left is hi(a) = inf against an
+// element of the other operand whose lo is exactly 0 (one fp32 value in 8192): inf * 0 = nan where fp32 gives inf.
 __device__ __forceinline__ float tf32_lo_of(float x) {
     const uint32_t b = __float_as_uint(x);
     const float d = __fsub_rn(x, __uint_as_float(b & 0xFFFFE000u));
-    const uint32_t r = (__float_as_uint(d) + 0x1000u) & 0xFFFFE000u;
+    const uint32_t r = __float_as_uint(d) + 0x1000u;   // the low 13 bits that remain are dropped by the tensor core
     return d == d ? __uint_as_float(r) : 0.0f;   // x = inf/nan gives d = nan
 }
 
@@ -291,7 +330,9 @@ __device__ __forceinline__ float tf32_lo_of(float x) {
 template <int CG, int MODE, int TN, bool AMN, bool BMN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
-    constexpr bool XFORM = MODE == MODE_XFORM;
+    constexpr bool TS = MODE == MODE_XFORM_TS;       // A operand (hi, lo) staged in tensor memory
+    constexpr bool XFORM = MODE == MODE_XFORM || TS;
+    static_assert(!TS || (CG == 1 && TN <= 128), "the TMEM-A variant is single-CTA and needs TMEM columns beside the accumulators");
     constexpr bool TO_LEADER = CG == 2 && !XFORM;   // whose `full` barrier the TMA copies signal
     constexpr int TILE_N = TN;
     constexpr int HALF_N = TN / 2;       // columns drained by one epilogue warp
@@ -300,9 +341,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int B_ROWS = b_rows<CG, TN>();
     constexpr int B_BYTES = b_bytes<CG, TN>();
     constexpr int RAW_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t IDESC = make_idesc_tf32(CG * 128, TILE_N, AMN, BMN);
+    constexpr uint32_t IDESC = make_idesc_tf32(CG * 128, TILE_N, TS ? false : AMN, BMN);   // A from TMEM is always [row][k]
     constexpr uint32_t KA = kstep_bytes<AMN>(), KB = kstep_bytes<BMN>();
     constexpr int TILE_ELEMS = TILE_M * TN;   // one CTA's share of a tile (workspace layout: [column][128 rows])
+    constexpr int TMEM_COLS = TS ? 512 : 2 * TILE_N;   // two accumulator buffers (+ STAGES slots of A for TS)
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ ChainParams s_chain;
@@ -367,7 +409,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int s = 0; s < STAGES; s++) {
                 mbar_init(full_bar(s), 1);
                 mbar_init(empty_bar(s), 1);
-                mbar_init(ready_bar(s), NUM_EPI_WARPS * CG);       // every transform (= epilogue) warp of the pair
+                mbar_init(ready_bar(s), TS ? NUM_EPI_WARPS / 2 : NUM_EPI_WARPS * CG);   // every transform (= epilogue) warp of the pair; TS: of one group
             }
             for (int b = 0; b < 2; b++) {
                 mbar_init(tmem_full_bar(b), 1);
@@ -376,7 +418,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<CG>(tmem_slot, 2 * TILE_N);
+        tmem_alloc<CG>(tmem_slot, TMEM_COLS);
     }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -390,8 +432,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ===================== TMA producer =====================
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
+#ifdef JZ_GEMM_PROFILE
+            long long pf_wait = 0, pf_t0 = clock64();
+#endif
             for (int kb = 0; kb < num_kb; kb++) {
+#ifdef JZ_GEMM_PROFILE
+                const long long pf_a = clock64();
+#endif
                 mbar_wait(empty_bar(stage), phase ^ 1);
+#ifdef JZ_GEMM_PROFILE
+                pf_wait += clock64() - pf_a;
+                if (kb == num_kb - 1 && blockIdx.x == 5 && blockIdx.z == 0)
+                    { args.prof[0] = num_kb; args.prof[1] = clock64() - pf_t0; args.prof[2] = pf_wait; }
+#endif
                 if (XFORM) mbar_arrive_expect_tx(full_bar(stage), uint32_t(RAW_BYTES));
                 else if (leader) mbar_arrive_expect_tx(full_bar(stage), uint32_t(STAGE_BYTES) * CG);
                 const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -406,35 +459,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (leader) {
             uint32_t stage = 0, phase = 0;
             int chunk = 0, in_chunk = 0;
+#ifdef JZ_GEMM_PROFILE
+            long long pf_ready = 0, pf_tmem = 0, pf_t0 = clock64();
+#endif
             for (int kb = 0; kb < num_kb; kb++) {
                 const uint32_t buf = uint32_t(chunk) & 1u;
+#ifdef JZ_GEMM_PROFILE
+                const long long pf_a = clock64();
+#endif
                 if (in_chunk == 0) {  // this TMEM buffer must have been drained by every epilogue warp
                     mbar_wait(tmem_empty_bar(buf), ((uint32_t(chunk) >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                 }
+#ifdef JZ_GEMM_PROFILE
+                const long long pf_b = clock64();
+#endif
                 mbar_wait(XFORM ? ready_bar(stage) : full_bar(stage), phase);
                 tc_fence_after();
+#ifdef JZ_GEMM_PROFILE
+                pf_tmem += pf_b - pf_a;
+                pf_ready += clock64() - pf_b;
+                if (kb == num_kb - 1 && blockIdx.x == 5 && blockIdx.z == 0 && (threadIdx.x & 31) == 0)
+                    { args.prof[3] = clock64() - pf_t0; args.prof[4] = pf_ready; args.prof[5] = pf_tmem; }
+#endif
                 const bool chunk_end = (in_chunk == kbc - 1) || (kb == num_kb - 1);
                 if (elect_one()) {
                     const uint32_t d = tmem_base + buf * TILE_N;
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                    const uint32_t a_hi = sa, b_hi = sa + A_BYTES;
-                    const uint32_t a_lo = sa + RAW_BYTES, b_lo = sa + RAW_BYTES + A_BYTES;
                     uint32_t acc = in_chunk == 0 ? 0u : 1u;
-                    if (XFORM) {
+                    if constexpr (TS) {
+                        // A: TMEM slot of this stage (columns [0,32) = raw words, the tensor core reads their top 19
+                        // bits = hi; [32,64) = lo); B: raw tile and lo(B) in the smem stage
+                        const uint32_t a_t = tmem_base + uint32_t(2 * TILE_N + int(stage) * TS_SLOT_COLS);
+                        const uint32_t b_hi = sa + A_BYTES, b_lo = sa + A_BYTES + B_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ks++) {
-                            umma_tf32<CG>(d, make_smem_desc<AMN>(a_lo + ks * KA), make_smem_desc<BMN>(b_hi + ks * KB), IDESC, acc);
+                            umma_tf32_ts(d, a_t + BK + ks * UMMA_K, make_smem_desc<BMN>(b_hi + ks * KB), IDESC, acc);
                             acc = 1u;
                         }
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ks++)
-                            umma_tf32<CG>(d, make_smem_desc<AMN>(a_hi + ks * KA), make_smem_desc<BMN>(b_lo + ks * KB), IDESC, 1u);
-                    }
+                            umma_tf32_ts(d, a_t + ks * UMMA_K, make_smem_desc<BMN>(b_lo + ks * KB), IDESC, 1u);
 #pragma unroll
-                    for (int ks = 0; ks < BK / UMMA_K; ks++) {
-                        umma_tf32<CG>(d, make_smem_desc<AMN>(a_hi + ks * KA), make_smem_desc<BMN>(b_hi + ks * KB), IDESC, acc);
-                        acc = 1u;
+                        for (int ks = 0; ks < BK / UMMA_K; ks++)
+                            umma_tf32_ts(d, a_t + ks * UMMA_K, make_smem_desc<BMN>(b_hi + ks * KB), IDESC, 1u);
+                    } else {
+                        const uint32_t a_hi = sa, b_hi = sa + A_BYTES;
+                        const uint32_t a_lo = sa + RAW_BYTES, b_lo = sa + RAW_BYTES + A_BYTES;
+                        if (XFORM) {
+#pragma unroll
+                            for (int ks = 0; ks < BK / UMMA_K; ks++) {
+                                umma_tf32<CG>(d, make_smem_desc<AMN>(a_lo + ks * KA), make_smem_desc<BMN>(b_hi + ks * KB), IDESC, acc);
+                                acc = 1u;
+                            }
+#pragma unroll
+                            for (int ks = 0; ks < BK / UMMA_K; ks++)
+                                umma_tf32<CG>(d, make_smem_desc<AMN>(a_hi + ks * KA), make_smem_desc<BMN>(b_lo + ks * KB), IDESC, 1u);
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < BK / UMMA_K; ks++) {
+                            umma_tf32<CG>(d, make_smem_desc<AMN>(a_hi + ks * KA), make_smem_desc<BMN>(b_hi + ks * KB), IDESC, acc);
+                            acc = 1u;
+                        }
                     }
                     umma_commit<CG>(empty_bar(stage));                   // frees this smem stage (both CTAs)
                     if (chunk_end) umma_commit<CG>(tmem_full_bar(buf));  // chunk accumulator complete
@@ -469,14 +555,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         static_assert(N4 % XT == 0 && PER % BATCH == 0, "stage size must divide evenly among the transform threads");
         const int te = threadIdx.x - 32 * FIRST_EPI_WARP;
         uint32_t stage = 0, phase = 0;
+        uint32_t pend_ready = 0;   // TS: `ready` barrier of the group's transformed but not yet handed-over k-block
+        constexpr bool DEFER = TS && STAGES >= 6;
         int next_drain = 0;
         const int kb_end = XFORM ? num_kb : 0;
+#ifdef JZ_GEMM_PROFILE
+        long long pf_full = 0, pf_xf = 0, pf_dw = 0, pf_dr = 0, pf_t0 = clock64(), pf_own = 0, pf_skip = 0, pf_xa = 0, pf_xb = 0;
+#endif
         for (int kb = 0; kb <= kb_end; kb++) {
+#ifdef JZ_GEMM_PROFILE
+            const long long pf_it = clock64();
+#endif
+            if (TS && pend_ready && kb + 2 > kb_end && (kb >= kb_end || (kb & 1) != half)) {
+                // the group's last k-block: nothing left to hide its hand-over under.  (Drains of earlier iterations never
+                // wait on a pending hand-over: chunk c is drained at kb >= 4c + 4 + STAGES - 1 and the pending k-block
+                // is kb - 1 or kb - 2 > 4c + 3 for STAGES >= 3.)
+                tmem_st_wait();
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(pend_ready);
+                pend_ready = 0;
+            }
             while (next_drain < num_chunks && (kb >= kb_end || (next_drain + 1) * kbc + STAGES - 1 <= kb)) {
                 const int chunk = next_drain++;
                 const uint32_t buf = uint32_t(chunk) & 1u;
+#ifdef JZ_GEMM_PROFILE
+                const long long pf_a = clock64();
+#endif
                 mbar_wait(tmem_full_bar(buf), (uint32_t(chunk) >> 1) & 1u);
                 tc_fence_after();
+#ifdef JZ_GEMM_PROFILE
+                pf_dw += clock64() - pf_a;
+                pf_dr -= clock64();
+#endif
 #pragma unroll
                 for (int p = 0; p < HALF_N / 32; p++) {
                     uint32_t r[32];
@@ -487,26 +599,127 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(buf ? empty1 : empty0);  // on the leader CTA's barrier
+#ifdef JZ_GEMM_PROFILE
+                pf_dr += clock64();
+#endif
             }
             if (XFORM && kb < kb_end) {
-                mbar_wait(full_bar(stage), phase);
-                const float4* src = reinterpret_cast<const float4*>(gen_base + stage * STAGE_BYTES) + te;
-                float4* dst = reinterpret_cast<float4*>(gen_base + stage * STAGE_BYTES + RAW_BYTES) + te;
+                // TS: the two warp groups (half = 0 / 1, each with all four TMEM lane quarters) take alternate k-blocks, so
+                // two transforms are in flight and one's shared-memory / tcgen05.st latency hides under the other's
+                if (!TS || (kb & 1) == half) {
+#ifdef JZ_GEMM_PROFILE
+                    const long long pf_a = clock64();
+#endif
+                    mbar_wait(full_bar(stage), phase);
+#ifdef JZ_GEMM_PROFILE
+                    pf_full += clock64() - pf_a;
+                    pf_xf -= clock64();
+#endif
+                    if constexpr (TS) {
+                        // A: this thread's row (TMEM lane quarter * 32 + lane) from the swizzled tile -> raw words + lo
+                        // words -> the stage's TMEM slot.  The slot is free: the TMA that filled this stage waited for
+                        // the MMAs of its previous use.  The hand-over of a k-block to the MMA warp (tcgen05.wait::st,
+                        // fences, arrive) is DEFERRED until the first half of the group's next k-block sits in
+                        // registers, so the tensor-memory store latency hides under that work instead of ending the
+                        // per-k-block dependency chain (ablation: the stores + their wait were 28 % of the mainloop).
+                        const uint8_t* const sA = gen_base + stage * STAGE_BYTES;
+                        const uint32_t a_t = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(2 * TILE_N + int(stage) * TS_SLOT_COLS);
 #pragma unroll
-                for (int i0 = 0; i0 < PER; i0 += BATCH) {
-                    float4 v[BATCH];
+                        for (int h = 0; h < 2; h++) {
+                            uint32_t hi[16], lo[16];
+                            if constexpr (AMN) {
+                                // box `quarter` = these 32 rows; line k = 128 B of 32 consecutive rows, its four 32-byte
+                                // atoms XOR-swizzled by (k & 3): a warp reads one line per k, conflict-free
+                                const uint8_t* const box = sA + quarter * MN_BOX_BYTES;
 #pragma unroll
-                    for (int u = 0; u < BATCH; u++) v[u] = src[(i0 + u) * XT];
+                                for (int i = 0; i < 16; i++) {
+                                    const int k = h * 16 + i;
+                                    hi[i] = *reinterpret_cast<const uint32_t*>(box + k * 128 + ((((lane >> 3) ^ (k & 3)) << 5) | ((lane & 7) << 2)));
+                                }
+                            } else {
+                                // row r = 128 B of 32 k, its eight 16-byte chunks XOR-swizzled by (r & 7): a quarter warp
+                                // reads eight different chunk positions, conflict-free
+                                const int r = quarter * 32 + lane;
+                                const uint8_t* const rowp = sA + r * 128;
 #pragma unroll
-                    for (int u = 0; u < BATCH; u++)
-                        dst[(i0 + u) * XT] = make_float4(tf32_lo_of(v[u].x), tf32_lo_of(v[u].y), tf32_lo_of(v[u].z), tf32_lo_of(v[u].w));
+                                for (int q = 0; q < 4; q++) {
+                                    const uint4 w = *reinterpret_cast<const uint4*>(rowp + (((h * 4 + q) ^ (r & 7)) << 4));
+                                    hi[4 * q] = w.x; hi[4 * q + 1] = w.y; hi[4 * q + 2] = w.z; hi[4 * q + 3] = w.w;
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; i++) lo[i] = __float_as_uint(tf32_lo_of(__uint_as_float(hi[i])));
+                            if (DEFER && h == 0 && pend_ready) {   // hand the group's previous k-block to the MMA warp
+                                tmem_st_wait();
+                                tc_fence_before();
+                                fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_cluster(pend_ready);
+                                pend_ready = 0;
+                            }
+                            tmem_st_32x32b_x16(a_t + h * 16, hi);
+                            tmem_st_32x32b_x16(a_t + BK + h * 16, lo);
+                        }
+                        // B: lo(B) beside the raw tile, by the 128 threads of this group
+                        constexpr int XG = XT / 2, PERG = B_BYTES / 16 / XG;
+                        static_assert(PERG % 4 == 0, "B tile must divide among the group's threads");
+                        const float4* src = reinterpret_cast<const float4*>(sA + A_BYTES) + (te & (XG - 1));
+                        float4* dst = reinterpret_cast<float4*>(gen_base + stage * STAGE_BYTES + A_BYTES + B_BYTES) + (te & (XG - 1));
+#pragma unroll
+                        for (int i0 = 0; i0 < PERG; i0 += 4) {
+                            float4 v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) v[u] = src[(i0 + u) * XG];
+#pragma unroll
+                            for (int u = 0; u < 4; u++)
+                                dst[(i0 + u) * XG] = make_float4(tf32_lo_of(v[u].x), tf32_lo_of(v[u].y), tf32_lo_of(v[u].z), tf32_lo_of(v[u].w));
+                        }
+                        pend_ready = ready0 + 8u * stage;
+                        if (!DEFER) {   // few stages: a late hand-over would starve the TMA of free stages
+                            tmem_st_wait();
+                            tc_fence_before();
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(pend_ready);
+                            pend_ready = 0;
+                        }
+                    } else {
+                        const float4* src = reinterpret_cast<const float4*>(gen_base + stage * STAGE_BYTES) + te;
+                        float4* dst = reinterpret_cast<float4*>(gen_base + stage * STAGE_BYTES + RAW_BYTES) + te;
+#pragma unroll
+                        for (int i0 = 0; i0 < PER; i0 += BATCH) {
+                            float4 v[BATCH];
+#pragma unroll
+                            for (int u = 0; u < BATCH; u++) v[u] = src[(i0 + u) * XT];
+#pragma unroll
+                            for (int u = 0; u < BATCH; u++)
+                                dst[(i0 + u) * XT] = make_float4(tf32_lo_of(v[u].x), tf32_lo_of(v[u].y), tf32_lo_of(v[u].z), tf32_lo_of(v[u].w));
+                        }
+                    }
+                    if constexpr (!TS) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(ready0 + 8u * stage);
+                    }
+#ifdef JZ_GEMM_PROFILE
+                    pf_xf += clock64();
+#endif
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(ready0 + 8u * stage);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+#ifdef JZ_GEMM_PROFILE
+            if (!TS || (kb & 1) == half) pf_own += clock64() - pf_it; else pf_skip += clock64() - pf_it;
+#endif
         }
+#ifdef JZ_GEMM_PROFILE
+        if (blockIdx.x == 5 && blockIdx.z == 0 && lane == 0 && (e & 3) == 0)
+        {
+            long long* g = args.prof + 8 + 8 * (e >> 2);
+            g[0] = clock64() - pf_t0; g[1] = pf_full; g[2] = pf_xf; g[3] = pf_dw; g[4] = pf_dr; g[5] = pf_own; g[6] = pf_skip;
+            args.prof[27 + 2 * (e >> 2)] = pf_xa; args.prof[28 + 2 * (e >> 2)] = pf_xb;
+        }
+        const long long pf_e0 = clock64();
+#endif
         float* const Cb = args.C + size_t(bz) * args.strideC;
         const size_t ldc = args.ldc;
         if (split < 0) {
@@ -695,12 +908,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
         }
+#ifdef JZ_GEMM_PROFILE
+        if (blockIdx.x == 5 && blockIdx.z == 0 && lane == 0 && e == 0)
+            { args.prof[24] = clock64() - pf_e0; args.prof[25] = split; args.prof[26] = args.splits; }
+#endif
     }
 
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
-    if (warp == 1) tmem_dealloc<CG>(tmem_base, 2 * TILE_N);
+    if (warp == 1) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
 }
 
 // ======================================================================= persistent TF32 kernel
@@ -1178,10 +1395,12 @@ static int launch_tf32_persistent(const Operand& a, const Operand& b, const Gemm
     if (e != cudaSuccess) return cuda_fail(e, "gemm_tf32_persistent_kernel launch");
     return JZ_OK;
 }
+#ifdef JZ_GEMM_TC_PERSIST_IMPL   // only jz_gemm_tc_tf32_persist.cu instantiates the persistent kernels
 static int launch_tf32_persistent_major(const Operand& a, const Operand& b, const GemmArgs& args, cudaStream_t s) {
     if (a.mn) return b.mn ? launch_tf32_persistent<true, true>(a, b, args, s) : launch_tf32_persistent<true, false>(a, b, args, s);
     return b.mn ? launch_tf32_persistent<false, true>(a, b, args, s) : launch_tf32_persistent<false, false>(a, b, args, s);
 }
+#endif
 
 // operand majors are compile-time (they select TMA box shapes and descriptor layouts)
 template <int CG, int MODE, int TN>

@@ -234,6 +234,48 @@ def test_gemm_split_k_units(jz, port, mode, shape):
         assert rel_fro(fused.to_host(), want) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(8192, 1024, 32), (4096, 520, 48), (2048, 777, 64), (128, 4096, 1024), (100, 3000, 300),
+                                   (96, 2100, 2000)])
+def test_gemm_narrow_or_short_output_tmem_a_variant(jz, port, shape):
+    """3xTF32 products with n <= 64 or m <= 128 run on single-CTA tiles whose A operand (hi and lo parts) is staged in
+    TENSOR MEMORY by the transform warps (jz_gemm_tc.cuh, MODE_XFORM_TS): both source layouts of A (the transform reads the
+    swizzled tile per row), k tails, split-K, alpha/beta, fused chain, inf propagation, and equality of the result's
+    accuracy class with the shared-memory form."""
+    m, k, n = shape
+    rng = np.random.default_rng(3 * m + 7 * k + 13 * n)
+    P, Q = F(rng.standard_normal((m, k))), F(rng.standard_normal((k, n)))
+    truth = port.gemm(P, 0, Q, 0, f64=True).astype(np.float64)
+    L = jz.lib()
+    for ta in (0, 1):
+        for tb in (0, 1):
+            a, b = operands(jz, P, Q, ta, tb)
+            got = a.dot(b, mode=0).to_host()
+            assert L.jz_gemm_last_path() == 1
+            err = rel_fro(got, truth)
+            print(f"TMEM-A {shape} ta={ta} tb={tb} splits={L.jz_gemm_last_splits()} rel_fro={err:.3e}")
+            assert err < 3e-6, (shape, ta, tb, err)     # fp32 grade, well inside the 1e-5 bound
+            again = a.dot(b, mode=0).to_host()
+            assert np.array_equal(bits(got), bits(again))
+    C0 = F(rng.standard_normal((m, n)))
+    a, b, c = jz.CM(P), jz.CM(Q), jz.CM(C0)
+    jz._lib.check(L.jz_gemm(0, 0, m, n, k, 0.75, a.ptr, m, b.ptr, k, -0.5, c.ptr, m, 0, None))
+    assert rel_fro(c.to_host(), 0.75 * truth - 0.5 * C0) < 1e-5
+    steps = [("affine", float(np.float32(1.0 / k)), 0.0), ("tanh",)]
+    arr, ns = jz._lib.make_steps(steps)
+    fused = jz.CM.empty("f", m, n)
+    jz._lib.check(L.jz_gemm_chain(0, 0, m, n, k, 1.0, a.ptr, m, b.ptr, k, fused.ptr, m, arr, ns, 0, None))
+    assert rel_fro(fused.to_host(), np.tanh(truth / np.float32(1.0 * k))) < 1e-5
+    # an infinite entry of A gives +-inf / nan exactly where the fp32 product does (hi carries it, lo is forced to 0)
+    P2 = P.copy()
+    P2[m // 2, k // 3] = np.inf
+    # (columns positive with a non-zero low part: inf * lo(B) is nan when lo(B) is exactly 0, one fp32 value in 8192 --
+    # the known corner of every split-precision product, cuBLAS's 3xTF32 included)
+    Qp = ((np.abs(Q) + 0.5).astype(np.float32).view(np.uint32) | np.uint32(0x800)).view(np.float32)
+    got = jz.CM(P2).dot(jz.CM(F(Qp)), mode=0).to_host()
+    assert np.all(np.isposinf(got[m // 2, :])), "row with +inf times positive columns must be +inf"
+    assert np.all(np.isfinite(np.delete(got, m // 2, axis=0)))
+
+
 def test_gemm_wide_output_tiny_k(jz):
     """products with a very wide output and tiny m, k (w^T X, ones(1, d) * X ...) must not hit a grid.y
     limit on the small-product / SIMT kernels"""
