@@ -95,7 +95,7 @@ struct GemmArgs {
     // instrumented build (scripts/build_prof_lib.sh): cycle counts of CTA 5, read back by jz_debug_gemm_prof
     //   [0..2] TMA: k-blocks, total, waiting for a free stage      [3..5] MMA: total, waiting for operands, for a drained accumulator
     //   [8 + 8 g ..] transform group g (warp e = 4 g): mainloop, waiting for TMA, transform, waiting for a chunk, drain
-    //   [24..26] epilogue: cycles, split, splits
+    //   [24..26] epilogue: cycles, split, splits      [29..31] split epilogue: partial tile out, fence + barrier, ticket + wait
     long long* prof;
 #endif
 };
@@ -560,7 +560,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int next_drain = 0;
         const int kb_end = XFORM ? num_kb : 0;
 #ifdef JZ_GEMM_PROFILE
-        long long pf_full = 0, pf_xf = 0, pf_dw = 0, pf_dr = 0, pf_t0 = clock64(), pf_own = 0, pf_skip = 0, pf_xa = 0, pf_xb = 0;
+        long long pf_full = 0, pf_xf = 0, pf_dw = 0, pf_dr = 0, pf_t0 = clock64(), pf_own = 0, pf_skip = 0;
 #endif
         for (int kb = 0; kb <= kb_end; kb++) {
 #ifdef JZ_GEMM_PROFILE
@@ -716,7 +716,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         {
             long long* g = args.prof + 8 + 8 * (e >> 2);
             g[0] = clock64() - pf_t0; g[1] = pf_full; g[2] = pf_xf; g[3] = pf_dw; g[4] = pf_dr; g[5] = pf_own; g[6] = pf_skip;
-            args.prof[27 + 2 * (e >> 2)] = pf_xa; args.prof[28 + 2 * (e >> 2)] = pf_xb;
         }
         const long long pf_e0 = clock64();
 #endif
@@ -821,15 +820,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int c = 0; c < HALF_N; c++) __stcg(dst + c * TILE_M, acc[c]);
             }
+#ifdef JZ_GEMM_PROFILE
+            const long long pf_s1 = clock64();
+#endif
             __threadfence();
             epi_bar_sync();
             unsigned* const tk = args.tickets + split_tile;
+#ifdef JZ_GEMM_PROFILE
+            const long long pf_s2 = clock64();
+#endif
             if (te == 0) {
                 atomicAdd(tk, 1u);
                 while (ld_acquire_gpu(tk) < want) __nanosleep(20);
             }
             epi_bar_sync();
             __threadfence();
+#ifdef JZ_GEMM_PROFILE
+            if (blockIdx.x == 5 && blockIdx.z == 0 && te == 0) {
+                args.prof[29] = pf_s1 - pf_e0; args.prof[30] = pf_s2 - pf_s1; args.prof[31] = clock64() - pf_s2;
+            }
+#endif
             // slice: columns [c_begin, c_end) of this CTA's 128 rows; a thread owns 4 consecutive rows (128-bit loads of
             // the partials, which sit [column][128 rows]) and every 8th column; the S partials are added in split
             // order, UB columns (UB x S independent loads) at a time

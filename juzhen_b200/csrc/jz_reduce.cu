@@ -747,7 +747,8 @@ softmax_cluster_kernel(float* out, const float* a, const float* y, size_t rows, 
     }
 }
 
-// ---- very long columns (rows > 32768): a column is split into chunks of kLongChunk elements, one CTA each, that meet
+// ---- long columns (rows > 16384; JZ_SOFTMAX_LONG_MIN moves the threshold): a column is split into chunks of kLongChunk
+// elements, one CTA each, that meet
 // through global memory.  Every CTA keeps its chunk in registers (read ONCE), publishes its partial (max m_c,
 // z_c = sum exp(x - m_c)), takes a ticket on the column's counter and waits until all chunks of the column have
 // published; then M = max m_c, Z = sum z_c * exp(m_c - M) (chunk order: identical in every CTA) and the chunk is
@@ -807,14 +808,29 @@ __global__ void __launch_bounds__(256) softmax_chunks_kernel(float* out, const f
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(tickets + c) : "memory");
             if (seen < nchunks) __nanosleep(40);
         } while (seen < nchunks);
-        float M = -1e30f;
-        for (unsigned q = 0; q < nchunks; q++) M = fmaxf(M, __ldcg(pc + q).x);
-        float Z = 0.0f;
-        for (unsigned q = 0; q < nchunks; q++) {
-            const float2 p = __ldcg(pc + q);
-            Z += __fmul_rn(p.y, expf(__fadd_rn(-M, p.x)));
+    }
+    __syncthreads();
+    // combine the column's partials with the whole CTA: thread q takes chunk q (nchunks <= 256), two block reductions in
+    // a fixed tree, so every CTA of the column gets the same M and Z.  (One thread walking the list paid an L2 round
+    // trip per chunk, twice: 32 chunks at 262144 rows = ~10 us per CTA with its registers parked; 0.65 of the copy peak.)
+    {
+        const bool have = threadIdx.x < nchunks;
+        const float2 p = have ? __ldcg(pc + threadIdx.x) : make_float2(-1e30f, 0.0f);
+        float M = warp_reduce<MaxOp>(p.x);
+        if (lane == 0) red[warp] = M;
+        __syncthreads();
+        M = warp_reduce<MaxOp>(red[lane & 7]);
+        float Z = have ? __fmul_rn(p.y, expf(__fadd_rn(-M, p.x))) : 0.0f;
+        Z = warp_reduce<SumOp>(Z);
+        __syncthreads();
+        if (lane == 0) red[warp] = Z;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) t += red[w];
+            s_scale = __fmul_rn(expf(__fadd_rn(-M, m)), __fdiv_rn(1.0f, t));
         }
-        s_scale = __fmul_rn(expf(__fadd_rn(-M, m)), __fdiv_rn(1.0f, Z));
     }
     __syncthreads();
     const float scale = s_scale;
@@ -854,6 +870,8 @@ static int launch_softmax_long(float* out, const float* a, const float* y, size_
     unsigned* tickets = static_cast<unsigned*>(wg.p);
     float2* part = reinterpret_cast<float2*>(static_cast<char*>(wg.p) + ticket_bytes);
     JZ_CUDA(cudaMemsetAsync(tickets, 0, ticket_bytes, s));
+    // (equal shares of the column instead of fixed 8192-element chunks with a short last one measured slower, 0.84 against
+    // 0.94 of the copy peak at 65536 rows where both give the same chunks: the runtime chunk length costs the address arithmetic)
     JZ_LAUNCH(softmax_chunks_kernel, unsigned(nchunks * cols), 256, 0, s, out, a, y, part, tickets, rows, ld, unsigned(nchunks), mode, rnb);
     return JZ_OK;
 }
@@ -917,7 +935,11 @@ static int softmax_impl(float* out, const float* a, const float* y, size_t rows,
     const bool regs_base = vec && rows % 4 == 0 && aligned16(out) && (mode == 0 || aligned16(y));
     static const bool no_cluster_sm = std::getenv("JZ_SOFTMAX_NO_CLUSTER") != nullptr;
     static const bool use_cluster_sm = std::getenv("JZ_SOFTMAX_CLUSTER") != nullptr;   // the older DSMEM form, for comparison
-    if (regs_base && rows > 32768 && !use_cluster_sm && !no_cluster_sm && nchunks_ok(rows, cols))
+    static const size_t long_min = [] {
+        const char* e = std::getenv("JZ_SOFTMAX_LONG_MIN");
+        return e && *e ? size_t(std::atoll(e)) : size_t(16384);
+    }();
+    if (regs_base && rows > long_min && !use_cluster_sm && !no_cluster_sm && nchunks_ok(rows, cols))
         return launch_softmax_long(out, a, y, rows, cols, ld, mode, rnb, s);
     if (regs_base && rows > 32768 && rows <= 262144 && !no_cluster_sm) {   // column shared by a cluster (see the kernel)
         const size_t n4 = rows >> 2;

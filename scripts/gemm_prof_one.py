@@ -41,5 +41,5 @@ for arg in sys.argv[1:]:
     for grp in (0, 1):
         q = g[8 + 8 * grp:8 + 8 * grp + 5]
         q = g[8 + 8 * grp:8 + 8 * grp + 7]
-        print(f"    transform group {grp}: mainloop {q[0]} clk: waiting for TMA {q[1]}, transform {q[2]}, waiting for a chunk {q[3]}, drain {q[4]}; own iterations {q[5]}, skipped {q[6]}; stamps A {g[27 + 2 * grp]} B {g[28 + 2 * grp]}")
-    print(f"    epilogue {g[24]} clk (split {g[25]} of {g[26]})")
+        print(f"    transform group {grp}: mainloop {q[0]} clk: waiting for TMA {q[1]}, transform {q[2]}, waiting for a chunk {q[3]}, drain {q[4]}; own iterations {q[5]}, skipped {q[6]}")
+    print(f"    epilogue {g[24]} clk (split {g[25]} of {g[26]}): partial tile out {g[29]}, fence + barrier {g[30]}, ticket + waiting for the siblings {g[31]}")

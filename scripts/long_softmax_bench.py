@@ -9,7 +9,9 @@ L = jz.lib(); assert L.jz_init(0) == 0
 stream = torch.cuda.current_stream().cuda_stream; jz.set_stream(stream)
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
 tag = "no-prefetch" if os.environ.get("JZ_SOFTMAX_NO_PREFETCH") else ("three-pass" if os.environ.get("JZ_SOFTMAX_NO_CLUSTER") else "default")
-for rows, cols in ((8192, 32768), (16384, 16384), (24576, 8192), (32768, 8192), (65536, 4096), (131072, 2048), (262144, 1024)):
+if os.environ.get("JZ_SOFTMAX_LONG_MIN"): tag += f", chunked above {os.environ['JZ_SOFTMAX_LONG_MIN']} rows"
+for rows, cols in ((8192, 32768), (12288, 16384), (16384, 16384), (20480, 8192), (24576, 8192), (32768, 8192), (49152, 4096), (65536, 4096),
+                   (131072, 2048), (262144, 1024)):
     x, y = jz.CM.randn(rows, cols, seed=1), jz.CM.empty("y", rows, cols)
     f = lambda: L.jz_softmax_cols(y.ptr, x.ptr, rows, cols, rows, stream)
     for _ in range(3): f()
