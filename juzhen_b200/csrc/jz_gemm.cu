@@ -617,6 +617,8 @@ int jz_gemm_last_splits(void) { return ctx().gemm_last_splits; }
 // instrumented builds only (not declared in include/jz_b200.h): the cycle counters of the last tensor-core GEMM launch
 extern "C" __attribute__((visibility("default"))) int jz_debug_gemm_prof(long long* out32) {
     cudaDeviceSynchronize();
-    return cudaMemcpy(out32, jz::tc::prof_buf(), sizeof(long long) * 32, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+    const bool ok = cudaMemcpy(out32, jz::tc::prof_buf(), sizeof(long long) * 32, cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaMemset(jz::tc::prof_buf(), 0, sizeof(long long) * 32);   // roles that do not exist in the next launch's CTA 5 read as 0
+    return ok ? 0 : 1;
 }
 #endif

@@ -35,6 +35,9 @@ for stage in "$@"; do
       timeout -k 5 1200 python scripts/gemm_sweep.py ${arg//,/ } 2>&1 | tee gpurun_out/${TAG}_gemm_sweep.log | grep -v '^{' ;;
     shapes)
       timeout -k 5 900 python scripts/gemm_shapes.py 2>&1 | tee gpurun_out/${TAG}_gemm_shapes.log ;;
+    prof)
+      JZ_B200_LIB=build/prof/libjz_b200.so timeout -k 5 300 python scripts/gemm_prof_one.py 8192,32,8192 8192,32,8192,1,0 128,1024,60000,0,1 \
+        1024,1024,1024 1536,1536,1536 2048,2048,2048,0,0,1 4096,4096,4096 2>&1 | grep -v '^$' | tee gpurun_out/${TAG}_gemm_prof.log ;;
     bench)
       timeout -k 5 1500 python bench.py --impl reference 2>gpurun_out/${TAG}_bench_reference.err | tail -1 > gpurun_out/${TAG}_bench_reference.json
       timeout -k 5 1500 python bench.py 2>gpurun_out/${TAG}_bench.err | tail -1 > gpurun_out/${TAG}_bench.json
