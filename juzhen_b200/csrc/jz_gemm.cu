@@ -15,6 +15,7 @@
 // rank-1 products (k == 1: the reference's broadcast idiom) are a streaming outer-product kernel.
 #include <cuda.h>
 
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
@@ -338,6 +339,26 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         args.tiles_m = unsigned(ceil_div(m, size_t(cg * TILE_M)));
         args.tiles_n = unsigned(ceil_div(n, size_t(tn)));
         plan_units(args, cg, split3x, batch);
+        if (split3x && f_ts < 0 && !ts && cg == 2 && tn == 256 && batch == 1 &&
+            size_t(args.tiles_m) * args.tiles_n <= size_t(ctx().sm_count) / 4) {
+            // A 3xTF32 product of fewer 256 x 256 tiles than half the CTA pairs: it either splits every tile along k (and
+            // pays ~18 kclk for the partials' trip through L2) or leaves SMs idle.  128 x 128 TMEM-A tiles on single CTAs
+            // cover the chip without (or with fewer) splits; they cost more per k-block and per output element, so they win
+            // only while k is short.  Cycle estimates fitted to profiles/r02f_gemm_tile_plans.log (1024^3 22.3 -> 20.7 us,
+            // 1280^3 36.1 -> 31.5, 1536^3 40.3 -> 36.2; 1024 x 784 x 8192 stays on pairs: 73 against 99 us).
+            GemmArgs alt = args;
+            alt.tiles_m = unsigned(ceil_div(m, size_t(TILE_M)));
+            alt.tiles_n = unsigned(ceil_div(n, size_t(128)));
+            plan_units(alt, 1, split3x, batch);
+            const double units_alt = double(alt.full_tiles) + double(alt.tiles_m * alt.tiles_n - alt.full_tiles) * alt.splits;
+            const double waves_alt = std::ceil(units_alt / double(ctx().sm_count));
+            const double t_pair = double(args.kb_per_split) * (args.kb_per_split >= 32 ? 1650.0 : 2100.0) + (args.splits > 1 ? 18000.0 : 6000.0);
+            const double t_alt = waves_alt * double(alt.kb_per_split) * 1350.0 + (alt.splits > 1 ? 9000.0 : 3000.0);
+            if (t_alt < t_pair) {
+                args = alt;
+                ts = true; cg = 1; tn = 128;
+            }
+        }
         if (args.splits == 1 && cg == 2 && tn == 256 && batch == 1 &&
             size_t(args.tiles_m) * args.tiles_n * 2 <= size_t(ctx().sm_count) / 2) {
             // a small grid that is not worth splitting along k: narrow tiles at least double the number of busy SM pairs
