@@ -16,6 +16,10 @@
 //   * 3xTF32 (MODE_XFORM, fp32 accuracy): every k-block issues A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same
 //     TMEM accumulator.  kind::tf32 reads fp32 words and drops the low 13 mantissa bits, so the raw tile already IS
 //     the hi operand; the epilogue warps compute lo = rna_tf32(x - trunc_tf32(x)) into a second shared buffer;
+//   * 3xTF32 with A in TENSOR MEMORY (MODE_XFORM_TS, CG = 1, TN <= 128: narrow / short outputs and small products of
+//     few tiles, where the shared-memory transform and not the tensor pipe sets the pace): the transform warps read A's
+//     rows from the swizzled tile, write raw words and lo words to TMEM (tcgen05.st, one slot per stage beside the two
+//     accumulator buffers) and the MMAs take A from TMEM (tcgen05.mma [d], [a], b_desc); B keeps the shared form;
 //   * two-level accumulation: only kb_per_chunk k-blocks are chained inside TMEM (the tensor core accumulates with
 //     truncation), the epilogue warps add each chunk into fp32 registers with round-to-nearest while the MMA warp
 //     fills the other TMEM half;
@@ -70,6 +74,10 @@ template <int CG, int MODE, int TN> __host__ __device__ constexpr int num_stages
     }
     return s > 8 ? 8 : s;
 }
+// TMEM-A variant: two transform groups of four warps (one per TMEM lane quarter) take the k-blocks alternately.  (A third,
+// transform-only group of four more warps was measured at TN = 64: 73.6 against 73.0 us at 8192 x 32 x 8192 -- the
+// transform is bound by what the groups share, tensor-memory store and integer-pipe throughput, not by a warp's latency.)
+constexpr int TS_GROUPS = 2;
 template <int CG, int MODE, int TN> __host__ __device__ constexpr int smem_bytes() {
     return num_stages<CG, MODE, TN>() * stage_bytes<CG, MODE, TN>() + 1024 /*align slack*/ + 256 /*barriers*/;
 }
@@ -345,6 +353,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr uint32_t KA = kstep_bytes<AMN>(), KB = kstep_bytes<BMN>();
     constexpr int TILE_ELEMS = TILE_M * TN;   // one CTA's share of a tile (workspace layout: [column][128 rows])
     constexpr int TMEM_COLS = TS ? 512 : 2 * TILE_N;   // two accumulator buffers (+ STAGES slots of A for TS)
+    constexpr int GROUPS = TS ? TS_GROUPS : 1;   // transform groups taking k-blocks round-robin
+    constexpr bool DEFER = TS && STAGES >= 6;   // hand a k-block to the MMA warp only when the group's next one is in registers
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ ChainParams s_chain;
@@ -427,6 +437,75 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // everything above touched no global memory: it may run while the previous kernel of the stream drains
     pdl_wait();
     pdl_launch_dependents();
+
+    // hand a transformed k-block to the MMA warp: tensor-memory stores retired, generic-proxy writes of lo(B) visible
+    // to the tensor core, one arrive per warp on the stage's `ready` barrier
+    auto ts_hand_over = [&](uint32_t& pend_ready) {
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(pend_ready);
+        pend_ready = 0;
+    };
+    // TMEM-A transform of one landed stage by one group of four warps (`quarter` = the warp's TMEM lane quarter, `tg` = the
+    // thread's index in the group).  A: this thread's row (quarter * 32 + lane) from the swizzled tile -> raw words + lo
+    // words -> the stage's TMEM slot.  The slot is free: the TMA that filled this stage waited for the MMAs of its previous
+    // use.  With DEFER the hand-over of a k-block waits until the first half of the group's NEXT k-block sits in registers,
+    // so the tensor-memory store latency hides under that work instead of ending the per-k-block dependency chain
+    // (ablation: the stores + their wait were 28 % of the mainloop).
+    auto ts_transform = [&](uint32_t stage, int quarter, int tg, uint32_t ready0, uint32_t& pend_ready) {
+        if constexpr (TS) {
+            const int lane = threadIdx.x & 31;
+            const uint8_t* const sA = gen_base + stage * STAGE_BYTES;
+            const uint32_t a_t = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(2 * TILE_N + int(stage) * TS_SLOT_COLS);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t hi[16], lo[16];
+                if constexpr (AMN) {
+                    // box `quarter` = these 32 rows; line k = 128 B of 32 consecutive rows, its four 32-byte atoms
+                    // XOR-swizzled by (k & 3): a warp reads one line per k, conflict-free
+                    const uint8_t* const box = sA + quarter * MN_BOX_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int k = h * 16 + i;
+                        hi[i] = *reinterpret_cast<const uint32_t*>(box + k * 128 + ((((lane >> 3) ^ (k & 3)) << 5) | ((lane & 7) << 2)));
+                    }
+                } else {
+                    // row r = 128 B of 32 k, its eight 16-byte chunks XOR-swizzled by (r & 7): a quarter warp reads eight
+                    // different chunk positions, conflict-free
+                    const int r = quarter * 32 + lane;
+                    const uint8_t* const rowp = sA + r * 128;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(rowp + (((h * 4 + q) ^ (r & 7)) << 4));
+                        hi[4 * q] = w.x; hi[4 * q + 1] = w.y; hi[4 * q + 2] = w.z; hi[4 * q + 3] = w.w;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) lo[i] = __float_as_uint(tf32_lo_of(__uint_as_float(hi[i])));
+                if (DEFER && h == 0 && pend_ready) ts_hand_over(pend_ready);   // the group's previous k-block
+                tmem_st_32x32b_x16(a_t + h * 16, hi);
+                tmem_st_32x32b_x16(a_t + BK + h * 16, lo);
+            }
+            // B: lo(B) beside the raw tile, by the 128 threads of this group
+            constexpr int XG = 128, PERG = B_BYTES / 16 / XG;
+            static_assert(PERG % 4 == 0, "B tile must divide among the group's threads");
+            const float4* src = reinterpret_cast<const float4*>(sA + A_BYTES) + tg;
+            float4* dst = reinterpret_cast<float4*>(gen_base + stage * STAGE_BYTES + A_BYTES + B_BYTES) + tg;
+#pragma unroll
+            for (int i0 = 0; i0 < PERG; i0 += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = src[(i0 + u) * XG];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    dst[(i0 + u) * XG] = make_float4(tf32_lo_of(v[u].x), tf32_lo_of(v[u].y), tf32_lo_of(v[u].z), tf32_lo_of(v[u].w));
+            }
+            pend_ready = ready0 + 8u * stage;
+            if (!DEFER) ts_hand_over(pend_ready);   // few stages: a late hand-over would starve the TMA of free stages
+        }
+    };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -556,7 +635,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int te = threadIdx.x - 32 * FIRST_EPI_WARP;
         uint32_t stage = 0, phase = 0;
         uint32_t pend_ready = 0;   // TS: `ready` barrier of the group's transformed but not yet handed-over k-block
-        constexpr bool DEFER = TS && STAGES >= 6;
         int next_drain = 0;
         const int kb_end = XFORM ? num_kb : 0;
 #ifdef JZ_GEMM_PROFILE
@@ -566,16 +644,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #ifdef JZ_GEMM_PROFILE
             const long long pf_it = clock64();
 #endif
-            if (TS && pend_ready && kb + 2 > kb_end && (kb >= kb_end || (kb & 1) != half)) {
-                // the group's last k-block: nothing left to hide its hand-over under.  (Drains of earlier iterations never
-                // wait on a pending hand-over: chunk c is drained at kb >= 4c + 4 + STAGES - 1 and the pending k-block
-                // is kb - 1 or kb - 2 > 4c + 3 for STAGES >= 3.)
-                tmem_st_wait();
-                tc_fence_before();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(pend_ready);
-                pend_ready = 0;
+            if (TS && pend_ready && kb + (half - kb % GROUPS + GROUPS) % GROUPS >= kb_end) {
+                // the group has no further k-block: nothing left to hide the hand-over of its last one under.  (Drains of
+                // earlier iterations never wait on a pending hand-over: chunk c is drained at kb >= 4c + 4 + STAGES - 1 and
+                // a pending k-block is at most GROUPS behind kb, i.e. > 4c + 3 for STAGES > GROUPS.)
+                ts_hand_over(pend_ready);
             }
             while (next_drain < num_chunks && (kb >= kb_end || (next_drain + 1) * kbc + STAGES - 1 <= kb)) {
                 const int chunk = next_drain++;
@@ -604,9 +677,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #endif
             }
             if (XFORM && kb < kb_end) {
-                // TS: the two warp groups (half = 0 / 1, each with all four TMEM lane quarters) take alternate k-blocks, so
-                // two transforms are in flight and one's shared-memory / tcgen05.st latency hides under the other's
-                if (!TS || (kb & 1) == half) {
+                // TS: the two warp groups (half = 0 / 1, each with all four TMEM lane quarters) take the k-blocks alternately,
+                // so two transforms are in flight and one's shared-memory / tcgen05.st latency hides under the other's
+                if (!TS || kb % GROUPS == half) {
 #ifdef JZ_GEMM_PROFILE
                     const long long pf_a = clock64();
 #endif
@@ -616,73 +689,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     pf_xf -= clock64();
 #endif
                     if constexpr (TS) {
-                        // A: this thread's row (TMEM lane quarter * 32 + lane) from the swizzled tile -> raw words + lo
-                        // words -> the stage's TMEM slot.  The slot is free: the TMA that filled this stage waited for
-                        // the MMAs of its previous use.  The hand-over of a k-block to the MMA warp (tcgen05.wait::st,
-                        // fences, arrive) is DEFERRED until the first half of the group's next k-block sits in
-                        // registers, so the tensor-memory store latency hides under that work instead of ending the
-                        // per-k-block dependency chain (ablation: the stores + their wait were 28 % of the mainloop).
-                        const uint8_t* const sA = gen_base + stage * STAGE_BYTES;
-                        const uint32_t a_t = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(2 * TILE_N + int(stage) * TS_SLOT_COLS);
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            uint32_t hi[16], lo[16];
-                            if constexpr (AMN) {
-                                // box `quarter` = these 32 rows; line k = 128 B of 32 consecutive rows, its four 32-byte
-                                // atoms XOR-swizzled by (k & 3): a warp reads one line per k, conflict-free
-                                const uint8_t* const box = sA + quarter * MN_BOX_BYTES;
-#pragma unroll
-                                for (int i = 0; i < 16; i++) {
-                                    const int k = h * 16 + i;
-                                    hi[i] = *reinterpret_cast<const uint32_t*>(box + k * 128 + ((((lane >> 3) ^ (k & 3)) << 5) | ((lane & 7) << 2)));
-                                }
-                            } else {
-                                // row r = 128 B of 32 k, its eight 16-byte chunks XOR-swizzled by (r & 7): a quarter warp
-                                // reads eight different chunk positions, conflict-free
-                                const int r = quarter * 32 + lane;
-                                const uint8_t* const rowp = sA + r * 128;
-#pragma unroll
-                                for (int q = 0; q < 4; q++) {
-                                    const uint4 w = *reinterpret_cast<const uint4*>(rowp + (((h * 4 + q) ^ (r & 7)) << 4));
-                                    hi[4 * q] = w.x; hi[4 * q + 1] = w.y; hi[4 * q + 2] = w.z; hi[4 * q + 3] = w.w;
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 16; i++) lo[i] = __float_as_uint(tf32_lo_of(__uint_as_float(hi[i])));
-                            if (DEFER && h == 0 && pend_ready) {   // hand the group's previous k-block to the MMA warp
-                                tmem_st_wait();
-                                tc_fence_before();
-                                fence_proxy_async_smem();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive_cluster(pend_ready);
-                                pend_ready = 0;
-                            }
-                            tmem_st_32x32b_x16(a_t + h * 16, hi);
-                            tmem_st_32x32b_x16(a_t + BK + h * 16, lo);
-                        }
-                        // B: lo(B) beside the raw tile, by the 128 threads of this group
-                        constexpr int XG = XT / 2, PERG = B_BYTES / 16 / XG;
-                        static_assert(PERG % 4 == 0, "B tile must divide among the group's threads");
-                        const float4* src = reinterpret_cast<const float4*>(sA + A_BYTES) + (te & (XG - 1));
-                        float4* dst = reinterpret_cast<float4*>(gen_base + stage * STAGE_BYTES + A_BYTES + B_BYTES) + (te & (XG - 1));
-#pragma unroll
-                        for (int i0 = 0; i0 < PERG; i0 += 4) {
-                            float4 v[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) v[u] = src[(i0 + u) * XG];
-#pragma unroll
-                            for (int u = 0; u < 4; u++)
-                                dst[(i0 + u) * XG] = make_float4(tf32_lo_of(v[u].x), tf32_lo_of(v[u].y), tf32_lo_of(v[u].z), tf32_lo_of(v[u].w));
-                        }
-                        pend_ready = ready0 + 8u * stage;
-                        if (!DEFER) {   // few stages: a late hand-over would starve the TMA of free stages
-                            tmem_st_wait();
-                            tc_fence_before();
-                            fence_proxy_async_smem();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(pend_ready);
-                            pend_ready = 0;
-                        }
+                        ts_transform(stage, quarter, te & 127, ready0, pend_ready);
                     } else {
                         const float4* src = reinterpret_cast<const float4*>(gen_base + stage * STAGE_BYTES) + te;
                         float4* dst = reinterpret_cast<float4*>(gen_base + stage * STAGE_BYTES + RAW_BYTES) + te;
@@ -708,7 +715,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
 #ifdef JZ_GEMM_PROFILE
-            if (!TS || (kb & 1) == half) pf_own += clock64() - pf_it; else pf_skip += clock64() - pf_it;
+            if (!TS || kb % GROUPS == half) pf_own += clock64() - pf_it; else pf_skip += clock64() - pf_it;
 #endif
         }
 #ifdef JZ_GEMM_PROFILE
