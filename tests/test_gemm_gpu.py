@@ -235,7 +235,7 @@ def test_gemm_split_k_units(jz, port, mode, shape):
 
 
 @pytest.mark.parametrize("shape", [(8192, 1024, 32), (4096, 520, 48), (2048, 777, 64), (128, 4096, 1024), (100, 3000, 300),
-                                   (96, 2100, 2000)])
+                                   (96, 2100, 2000), (16384, 40, 64), (128, 64, 8192), (16384, 96, 48), (1280, 1280, 1280)])
 def test_gemm_narrow_or_short_output_tmem_a_variant(jz, port, shape):
     """3xTF32 products with n <= 64 or m <= 128 run on single-CTA tiles whose A operand (hi and lo parts) is staged in
     TENSOR MEMORY by the transform warps (jz_gemm_tc.cuh, MODE_XFORM_TS): both source layouts of A (the transform reads the
