@@ -35,6 +35,7 @@ __device__ __forceinline__ float fold_warps(float v, float (*red)[32], F f, floa
 // the reference.  ml/layer.hpp:2373-2398 (+ causal_mask_kernel :2400-2412 fused as a flag).
 template <bool CAUSAL, bool STAGED, int W>
 __global__ void __launch_bounds__(32 * W) softmax_rows_kernel(float* y, const float* x, int S, float mask_val) {
+    pdl_enter();
     extern __shared__ float tile[];   // [S][32] when STAGED
     __shared__ float red[W][32];
     const int lane = threadIdx.x, w = threadIdx.y;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(32 * W) softmax_rows_kernel(float* y, const fl
 
 // s(a, b) = mask_val for b > a (ml/layer.hpp:2400-2412), in place, for callers that want the masked scores themselves
 __global__ void __launch_bounds__(256) causal_mask_kernel(float* s, size_t S, size_t total, float mask_val) {
+    pdl_enter();
     for (size_t idx = size_t(blockIdx.x) * 256 + threadIdx.x; idx < total; idx += size_t(gridDim.x) * 256) {
         const size_t local = idx % (S * S);
         if (local / S > local % S) s[idx] = mask_val;
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(256) causal_mask_kernel(float* s, size_t S, si
 // consumed with lanes along a.
 __global__ void __launch_bounds__(32 * AT_WARPS) softmax_rows_backward_kernel(float* dS, const float* A, const float* dAT,
                                                                               int S, float scale, unsigned row_blocks) {
+    pdl_enter();
     extern __shared__ float dtile[];   // [S][33]: dtile[b*33 + a_local] = dA(a0 + a_local, b)
     __shared__ float red[AT_WARPS][32];
     const int lane = threadIdx.x, w = threadIdx.y;
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(32 * AT_WARPS) softmax_rows_backward_kernel(fl
 // from L2).  The per-warp partial sums accumulate over the chunks in the same b order as the one-pass kernel.
 __global__ void __launch_bounds__(32 * AT_WARPS) softmax_rows_backward_long_kernel(float* dS, const float* A, const float* dAT,
                                                                                    int S, float scale, unsigned row_blocks, int chunk) {
+    pdl_enter();
     extern __shared__ float dtile[];   // [chunk][33]
     __shared__ float red[AT_WARPS][32];
     const int lane = threadIdx.x, w = threadIdx.y;
@@ -164,6 +168,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <bool VEC>
 __global__ void __launch_bounds__(32 * AT_WARPS) layernorm_forward_kernel(float* y, float* xhat, float* inv_std, const float* x,
                                                                           const float* gamma, const float* beta, int dim, size_t N) {
+    pdl_enter();
     const int lane = threadIdx.x;
     const size_t c = size_t(blockIdx.x) * AT_WARPS + threadIdx.y;
     if (c >= N) return;
@@ -216,6 +221,7 @@ __global__ void __launch_bounds__(32 * AT_WARPS) layernorm_forward_kernel(float*
 template <bool VEC>
 __global__ void __launch_bounds__(32 * AT_WARPS) layernorm_backward_kernel(float* dx, const float* dy, const float* gamma,
                                                                            const float* xhat, const float* inv_std, int dim, size_t N) {
+    pdl_enter();
     const int lane = threadIdx.x;
     const size_t c = size_t(blockIdx.x) * AT_WARPS + threadIdx.y;
     if (c >= N) return;

@@ -66,6 +66,7 @@ __device__ __forceinline__ void apply_tile(const UnaryF<JZ_LOG>&, float (&x)[N])
 
 template <class F>
 __global__ void __launch_bounds__(kThreads) map1_v4(float* out, const float* in, size_t n, F f) {
+    pdl_enter();
     const size_t n4 = n >> 2;
     const float4* in4 = reinterpret_cast<const float4*>(in);
     float4* out4 = reinterpret_cast<float4*>(out);
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(kThreads) map1_v4(float* out, const float* in,
 
 template <class F>
 __global__ void __launch_bounds__(kThreads) map1_s(float* out, const float* in, size_t n, F f) {
+    pdl_enter();
     const size_t tile = size_t(kThreads) * kUnroll;
     for (size_t base = size_t(blockIdx.x) * tile; base < n; base += size_t(gridDim.x) * tile) {
         float v[kUnroll];
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(kThreads) map1_s(float* out, const float* in, 
 
 template <class F>
 __global__ void __launch_bounds__(kThreads) map2_v4(float* out, const float* a, const float* b, size_t n, F f) {
+    pdl_enter();
     const size_t n4 = n >> 2;
     const float4* a4 = reinterpret_cast<const float4*>(a);
     const float4* b4 = reinterpret_cast<const float4*>(b);
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(kThreads) map2_v4(float* out, const float* a, 
 
 template <class F>
 __global__ void __launch_bounds__(kThreads) map2_s(float* out, const float* a, const float* b, size_t n, F f) {
+    pdl_enter();
     const size_t tile = size_t(kThreads) * kUnroll;
     for (size_t base = size_t(blockIdx.x) * tile; base < n; base += size_t(gridDim.x) * tile) {
         float x[kUnroll], y[kUnroll];
@@ -161,6 +165,7 @@ __global__ void __launch_bounds__(kThreads) map2_s(float* out, const float* a, c
 }
 
 __global__ void __launch_bounds__(kThreads) fill_v4(float* out, size_t n, float val) {
+    pdl_enter();
     const size_t n4 = n >> 2;
     float4* out4 = reinterpret_cast<float4*>(out);
     const float4 v = make_float4(val, val, val, val);
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(kThreads) fill_v4(float* out, size_t n, float 
 }
 
 __global__ void __launch_bounds__(kThreads) fill_s(float* out, size_t n, float val) {
+    pdl_enter();
     for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += size_t(gridDim.x) * kThreads)
         out[i] = val;
 }
@@ -183,6 +189,7 @@ __global__ void __launch_bounds__(kThreads) fill_s(float* out, size_t n, float v
 // fused chain: UNROLL x 4 values per thread in registers, every step applied to the
 // whole register tile so the per-step dispatch is amortised over 16 elements.
 __global__ void __launch_bounds__(kThreads) chain_v4(float* out, const float* in, size_t n, ChainParams cp) {
+    pdl_enter();
     __shared__ ChainParams c;
     stage_chain(&c, cp, threadIdx.x);
     __syncthreads();
@@ -215,6 +222,7 @@ __global__ void __launch_bounds__(kThreads) chain_v4(float* out, const float* in
 }
 
 __global__ void __launch_bounds__(kThreads) chain_s(float* out, const float* in, size_t n, ChainParams cp) {
+    pdl_enter();
     __shared__ ChainParams c;
     stage_chain(&c, cp, threadIdx.x);
     __syncthreads();
@@ -242,6 +250,7 @@ __device__ __forceinline__ void adam_elem(float& g, float& m, float& v, const Ad
     g = __fmul_rn(__fadd_rn(__fmul_rn(p.alpha, mh), 0.0f), __frcp_rn(den));   // (float)(1.0 / den): innocuous double rounding
 }
 __global__ void __launch_bounds__(kThreads) adam_v4(float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n, AdamP p) {
+    pdl_enter();
     const size_t n4 = n >> 2;
     float4* g4 = reinterpret_cast<float4*>(g);
     float4* m4 = reinterpret_cast<float4*>(m);
@@ -270,7 +279,8 @@ __global__ void __launch_bounds__(kThreads) adam_v4(float* __restrict__ g, float
         adam_elem(g[i], m[i], v[i], p);
     }
 }
-__global__ void __launch_bounds__(kThreads) adam_s(float* g, float* m, float* v, size_t n, AdamP p) {   // unaligned pointers
+__global__ void __launch_bounds__(kThreads) adam_s(float* g, float* m, float* v, size_t n, AdamP p) {
+    pdl_enter();   // unaligned pointers
     for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += size_t(gridDim.x) * kThreads) adam_elem(g[i], m[i], v[i], p);
 }
 
@@ -339,6 +349,7 @@ __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsig
 
 template <int OP>
 __global__ void ulp_sweep_kernel(uint32_t lo, uint32_t hi, unsigned long long* packed_max) {
+    pdl_enter();
     unsigned long long best = 0;
     for (uint64_t b = uint64_t(lo) + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; b < hi;
          b += uint64_t(gridDim.x) * blockDim.x) {

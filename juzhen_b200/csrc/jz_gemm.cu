@@ -38,6 +38,7 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_simt_kernel(size_t m, size_t n, size_t k, float alpha, const float* A,
                                                          size_t lda, const float* B, size_t ldb, float beta, float* C,
                                                          size_t ldc, ChainParams chain_p, unsigned gx) {
+    pdl_enter();
     __shared__ ChainParams chain;
     stage_chain(&chain, chain_p, threadIdx.x);
     __syncthreads();
@@ -128,6 +129,7 @@ static int launch_simt(int ta, int tb, size_t m, size_t n, size_t k, float alpha
 __global__ void __launch_bounds__(256) rank1_kernel(size_t m, size_t n, float alpha, const float* u, size_t su,
                                                     const float* v, size_t sv, float beta, float* C, size_t ldc,
                                                     ChainParams chain_p) {
+    pdl_enter();
     __shared__ ChainParams chain;
     stage_chain(&chain, chain_p, threadIdx.x);
     __syncthreads();
@@ -149,6 +151,7 @@ namespace tc {
 // K-major copy of an operand TMA cannot address in place (base or row pitch not 16-byte aligned).
 // source already K-major: src(r, kk) at r*ld + kk ; dst[r*kp + kk], one thread per quad of k, grid-stride.
 __global__ void __launch_bounds__(256) prep_kmajor_kernel(float* dst, size_t kp, const float* src, size_t ld, size_t rows, size_t k) {
+    pdl_enter();
     const size_t kq = kp >> 2;  // quads per row (kp is a multiple of 4)
     const size_t total = rows * kq;
     for (size_t idx = size_t(blockIdx.x) * 256 + threadIdx.x; idx < total; idx += size_t(gridDim.x) * 256) {
@@ -163,6 +166,7 @@ __global__ void __launch_bounds__(256) prep_kmajor_kernel(float* dst, size_t kp,
 // source MN-major: src(r, kk) at kk*ld + r ; dst[r*kp + kk]   (tiled transpose, 64 x 64 tiles through shared memory)
 __global__ void __launch_bounds__(256) prep_transpose_kernel(float* dst, size_t kp, const float* src, size_t ld, size_t rows,
                                                              size_t k, size_t tiles_r, size_t tiles_k) {
+    pdl_enter();
     __shared__ float tile[64][65];  // tile[kk][r]
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const size_t ntiles = tiles_r * tiles_k;
@@ -416,6 +420,7 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
 // replicate a finished m x n block (ldc) into every GPU's image through the multicast address (paths without a fused
 // multicast epilogue: SIMT / rank-1 / small products)
 __global__ void __launch_bounds__(256) mc_copy_kernel(float* mc, const float* src, size_t ldc, size_t m, size_t n) {
+    pdl_enter();
     for (size_t j = blockIdx.y; j < n; j += gridDim.y)
         for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < m; i += size_t(gridDim.x) * 256)
             asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc + j * ldc + i), "f"(src[j * ldc + i]) : "memory");

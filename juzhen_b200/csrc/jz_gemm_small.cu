@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(32 * SK_WARPS) gemm_small_kernel(size_t m, siz
                                                                    const float* __restrict__ B, size_t ldb, float beta,
                                                                    float* C, size_t ldc, ChainParams chain_p,
                                                                    size_t strideA, size_t strideB, size_t strideC, unsigned gx) {
+    pdl_enter();
     __shared__ ChainParams chain;
     __shared__ float red[KSPLIT ? SK_WARPS : 1][KSPLIT ? NT : 1][32];
     __shared__ __align__(16) float bline[SK_WARPS][2][32];   // per warp, two iterations deep

@@ -1331,13 +1331,7 @@ static int make_map(CUtensorMap* map, const Operand& op, size_t rows, size_t k, 
     return JZ_OK;
 }
 
-static bool pdl_enabled() {
-    static const bool on = [] {
-        const char* e = std::getenv("JZ_GEMM_NO_PDL");
-        return !(e && e[0] && e[0] != '0');
-    }();
-    return on;
-}
+static bool pdl_enabled() { return pdl_on(); }
 
 // args.tiles_m / tiles_n / full_tiles / splits / kb_per_split / ws / tickets are filled by the caller (plan_units)
 template <int CG, int MODE, int TN, bool AMN, bool BMN>

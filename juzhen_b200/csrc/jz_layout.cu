@@ -43,6 +43,7 @@ static Map2dGeom geom2d(size_t row_units, size_t cols) {
 // Op::run<VEC>(i, j): processes VEC consecutive rows starting at row i of column j.
 template <int VEC, class Op>
 __global__ void __launch_bounds__(256) map2d_kernel(Op op, size_t rows, size_t cols) {
+    pdl_enter();
     const size_t row_units = rows / VEC;
     for (size_t iu = size_t(blockIdx.x) * blockDim.x + threadIdx.x; iu < row_units;
          iu += size_t(gridDim.x) * blockDim.x) {
@@ -150,6 +151,7 @@ static int launch_map2d(const Op& op, size_t rows, size_t cols, bool vec_ok, cud
 __global__ void __launch_bounds__(kTile* kTileRows) transpose_kernel(float* dst, size_t ldd, const float* src,
                                                                      size_t lds, size_t rows, size_t cols,
                                                                      size_t tiles_i, size_t tiles_j) {
+    pdl_enter();
     __shared__ float tile[kTile][kTile + 1];
     const size_t ntiles = tiles_i * tiles_j;
     for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(kTile* kTileRows) transpose_kernel(float* dst,
 // Shared-memory pitch 65 keeps the transposed reads at most 2-way conflicted.
 __global__ void __launch_bounds__(256) transpose64_kernel(float* dst, size_t ldd, const float* src, size_t lds,
                                                           size_t rows, size_t cols, size_t tiles_i, size_t tiles_j) {
+    pdl_enter();
     __shared__ float tile[64][65];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const size_t ntiles = tiles_i * tiles_j;
@@ -222,6 +225,7 @@ template <bool TA, bool TB, class F>
 __global__ void __launch_bounds__(kTile* kTileRows) bin2d_t_kernel(float* out, size_t ldo, size_t rows, size_t cols,
                                                                    const float* a, size_t lda, const float* b,
                                                                    size_t ldb, F f, size_t tiles_i, size_t tiles_j) {
+    pdl_enter();
     __shared__ float ta[TA ? kTile : 1][kTile + 1];
     __shared__ float tb[TB ? kTile : 1][kTile + 1];
     const size_t ntiles = tiles_i * tiles_j;

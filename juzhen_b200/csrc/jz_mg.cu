@@ -33,6 +33,7 @@ struct FlagPtrs { unsigned* p[JZ_MAX_PEERS + 1]; };
 // One thread per rank; system-scope release / acquire so that everything the stream did before (kernel boundaries)
 // is visible to the peers' later kernels.
 __global__ void mg_barrier_kernel(FlagPtrs flags, int world, int rank, unsigned epoch) {
+    pdl_enter();
     const int r = threadIdx.x;
     if (r < world) {
         __threadfence_system();
@@ -48,6 +49,7 @@ __global__ void mg_barrier_kernel(FlagPtrs flags, int world, int rank, unsigned 
 
 // out[i] = sum over ranks (in rank order: every rank computes the same bits) of image_r[i]
 __global__ void __launch_bounds__(256) mg_allreduce_kernel(float* out, PeerPtrs img, int world, size_t n) {
+    pdl_enter();
     for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += size_t(gridDim.x) * 256) {
         float s = img.p[0][i];
         for (int r = 1; r < world; r++) s = __fadd_rn(s, img.p[r][i]);

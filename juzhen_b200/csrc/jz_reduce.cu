@@ -85,6 +85,7 @@ __device__ __forceinline__ void stage_columns(float* sm, const float* a, size_t 
 template <class Op>
 __global__ void __launch_bounds__(kShortCols) colreduce_short_kernel(float* out, const float* a, int rows,
                                                                      size_t cols, size_t ld, bool vec) {
+    pdl_enter();
     extern __shared__ float sm[];
     for (size_t c0 = size_t(blockIdx.x) * kShortCols; c0 < cols; c0 += size_t(gridDim.x) * kShortCols) {
         const int ncols = int(cols - c0 < size_t(kShortCols) ? cols - c0 : kShortCols);
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(kShortCols) colreduce_short_kernel(float* out,
 __global__ void __launch_bounds__(kShortCols) softmax_short_kernel(float* out, const float* a, const float* y,
                                                                    int rows, size_t cols, size_t ld, bool vec,
                                                                    int mode, float rnb) {
+    pdl_enter();
     extern __shared__ float sm[];
     for (size_t c0 = size_t(blockIdx.x) * kShortCols; c0 < cols; c0 += size_t(gridDim.x) * kShortCols) {
         const int ncols = int(cols - c0 < size_t(kShortCols) ? cols - c0 : kShortCols);
@@ -177,6 +179,7 @@ __device__ __forceinline__ float lane_reduce_span(const float* col, size_t len, 
 template <class Op, bool VEC>
 __global__ void __launch_bounds__(256) colreduce_warp_kernel(float* out, const float* a, size_t rows, size_t cols,
                                                              size_t ld) {
+    pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (size_t c = size_t(blockIdx.x) * 8 + warp; c < cols; c += size_t(gridDim.x) * 8) {
         float v = lane_reduce_span<Op, VEC>(a + c * ld, rows, lane);
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(256) colreduce_warp_kernel(float* out, const f
 template <class Op, bool VEC>
 __global__ void __launch_bounds__(256) colreduce_chunk_kernel(float* partial, const float* a, size_t rows,
                                                               size_t ld, size_t chunk_len, unsigned nchunks) {
+    pdl_enter();
     __shared__ float ws[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t c = blockIdx.y;
@@ -221,6 +225,7 @@ constexpr int kRowCluster = 8;   // CTAs per cluster along the column-chunk axis
 template <class Op, int VEC, bool CLUSTER>
 __global__ void __launch_bounds__(256) rowreduce_kernel(float* out, const float* a, size_t rows, size_t cols, size_t ld,
                                                         size_t cols_per_chunk, float* final_out, unsigned* tickets) {
+    pdl_enter();
     extern __shared__ float sm[];  // ty x (tx*VEC)
     const size_t row_units = rows / VEC;
     const size_t iu = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -332,6 +337,7 @@ __global__ void __launch_bounds__(256) rowreduce_kernel(float* out, const float*
 template <bool VEC>
 __global__ void __launch_bounds__(256) softmax_warp_kernel(float* out, const float* a, size_t rows, size_t cols,
                                                            size_t ld) {
+    pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (size_t c = size_t(blockIdx.x) * 8 + warp; c < cols; c += size_t(gridDim.x) * 8) {
         const float* col = a + c * ld;
@@ -368,6 +374,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 template <int NV, bool BLOCK, bool PREF = false>
 __global__ void __launch_bounds__(BLOCK ? 512 : 256)
 softmax_reg_kernel(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode, float rnb) {
+    pdl_enter();
     constexpr int G = BLOCK ? 512 : 32;
     static_assert(!PREF || BLOCK, "prefetch staging is for the CTA-per-column form");
     extern __shared__ float4 sm_stage[];   // PREF: [NV][512]
@@ -460,11 +467,13 @@ struct CeGradF {
 };
 template <class F>
 __global__ void __launch_bounds__(256) map2_inplace_kernel(float* out, const float* b, size_t n, F f) {
+    pdl_enter();
     for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += size_t(gridDim.x) * 256) out[i] = f(out[i], b[i]);
 }
 
 // ------------------------------------------------------------------ nrm2
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(double* partial, const float* x, size_t n, bool vec) {
+    pdl_enter();
     __shared__ double ws[8];
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     double acc = 0.0;
@@ -500,6 +509,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(double* partial, con
 }
 
 __global__ void nrm2_final_kernel(float* out, const double* partial, int n) {
+    pdl_enter();
     __shared__ double ws[32];
     double acc = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
@@ -671,6 +681,7 @@ static int reduce_entry(float* out, const float* a, size_t rows, size_t cols, si
 template <int NV, int CL>
 __global__ void __launch_bounds__(512)
 softmax_cluster_kernel(float* out, const float* a, const float* y, size_t rows, size_t cols, size_t ld, int mode, float rnb) {
+    pdl_enter();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float red[16];
@@ -760,6 +771,7 @@ constexpr int kLongChunk = 8192;   // elements per CTA: 8 float4 per thread
 
 __global__ void __launch_bounds__(256) softmax_chunks_kernel(float* out, const float* a, const float* y, float2* part, unsigned* tickets,
                                                              size_t rows, size_t ld, unsigned nchunks, int mode, float rnb) {
+    pdl_enter();
     __shared__ float red[8];
     __shared__ float s_scale;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -28,6 +28,7 @@ __device__ __forceinline__ void philox4x32_10(uint64_t index, uint64_t seed, uin
 
 template <bool NORMAL>
 __global__ void __launch_bounds__(256) rng_kernel(float* x, size_t n, uint64_t seed, uint64_t offset) {
+    pdl_enter();
     const size_t n4 = (n + 3) >> 2;
     for (size_t q = size_t(blockIdx.x) * 256 + threadIdx.x; q < n4; q += size_t(gridDim.x) * 256) {
         uint32_t r[4];

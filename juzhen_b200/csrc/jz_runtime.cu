@@ -28,6 +28,16 @@
 
 namespace jz {
 
+bool pdl_on() {
+    static const bool on = [] {
+        const char* e = std::getenv("JZ_NO_PDL");
+        const char* g = std::getenv("JZ_GEMM_NO_PDL");   // older name, still honoured
+        return !((e && e[0] && e[0] != '0') || (g && g[0] && g[0] != '0'));
+    }();
+    return on;
+}
+
+
 static Ctx g_ctx;
 static thread_local char g_err[512] = "";
 
