@@ -1312,7 +1312,38 @@ static EncodeTiledFn encode_fn() {
 // Tensor map of one operand over its source storage, zero OOB fill; third dimension = batch member.
 //   K-major ([rows][k], row stride `stride_elems`): dims {k, rows, batch}, box {32, box_rows, 1}, 128B swizzle.
 //   MN-major ([k][rows], k stride `stride_elems`): dims {rows, k, batch}, box {32 rows, 32 k, 1}, 128B swizzle / 32B atoms.
+// A training loop multiplies the same buffers step after step (the pool hands a temporary its old block back), and the
+// driver call costs about a microsecond of host time per operand on a launch-bound step: the encoded maps are kept in a
+// small per-thread direct-mapped cache keyed on everything the encoding depends on (the map holds no device state).
+struct MapKey {
+    const float* ptr; size_t rows, k, stride, batch_stride; int box_rows; unsigned batch; bool mn;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && k == o.k && stride == o.stride && batch_stride == o.batch_stride &&
+               box_rows == o.box_rows && batch == o.batch && mn == o.mn;
+    }
+};
+struct MapSlot { MapKey key; bool valid; alignas(64) CUtensorMap map; };
+static int make_map_uncached(CUtensorMap* map, const Operand& op, size_t rows, size_t k, int box_rows, unsigned batch);
 static int make_map(CUtensorMap* map, const Operand& op, size_t rows, size_t k, int box_rows, unsigned batch) {
+    constexpr size_t SLOTS = 64;
+    static thread_local MapSlot cache[SLOTS];
+    const MapKey key{op.ptr, rows, k, op.stride, op.batch_stride, box_rows, batch, op.mn};
+    size_t h = reinterpret_cast<uintptr_t>(op.ptr) >> 8;
+    h ^= (rows * 0x9E3779B97F4A7C15ull) ^ (k * 0xC2B2AE3D27D4EB4Full) ^ (size_t(box_rows) << 20) ^ (size_t(op.mn) << 40);
+    MapSlot& slot = cache[(h ^ (h >> 17) ^ (h >> 31)) % SLOTS];
+    if (slot.valid && slot.key == key) {
+        std::memcpy(map, &slot.map, sizeof(CUtensorMap));
+        return JZ_OK;
+    }
+    const int rc = make_map_uncached(map, op, rows, k, box_rows, batch);
+    if (rc == JZ_OK) {
+        slot.key = key;
+        std::memcpy(&slot.map, map, sizeof(CUtensorMap));
+        slot.valid = true;
+    }
+    return rc;
+}
+static int make_map_uncached(CUtensorMap* map, const Operand& op, size_t rows, size_t k, int box_rows, unsigned batch) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(JZ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const bool mn = op.mn;
