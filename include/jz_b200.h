@@ -197,6 +197,9 @@ int jz_gemm_strided_batched(int transA, int transB, size_t m, size_t n, size_t k
 int jz_gemm_last_path(void);
 /* k-splits per tile of the partial last wave in the last tensor-core launch (1 = no split-K units) */
 int jz_gemm_last_splits(void);
+/* 1 when those k-splits were the CTAs of one thread-block cluster per tile and exchanged their partial tiles through
+ * distributed shared memory (no workspace); 0 for the workspace + ticket form or no split */
+int jz_gemm_last_cluster_split(void);
 
 /* ---- multi-GPU, one process per GPU (SURVEY 8b jz_mg_*, 8e).  The reference has no collectives; these entry points
  *      give C / C++ callers the sharded forms without torch, NCCL or MPI inside the library: peers' buffers are mapped

@@ -338,7 +338,7 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
             return e && *e ? std::atoi(e) : -1;
         }();
         bool ts = split3x && f_ts != 0 && cg == 1;
-        if (split3x && f_ts == 2) { ts = true; cg = 1; tn = n <= 64 ? 64 : 128; }
+        if (split3x && f_ts == 2) { ts = true; cg = 1; tn = (n <= 64 || env_int("JZ_GEMM_TN") == 64) ? 64 : 128; }
         if (ts && tn == 256) tn = 128;
         args.tiles_m = unsigned(ceil_div(m, size_t(cg * TILE_M)));
         args.tiles_n = unsigned(ceil_div(n, size_t(tn)));
@@ -356,8 +356,17 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
             plan_units(alt, 1, split3x, batch);
             const double units_alt = double(alt.full_tiles) + double(alt.tiles_m * alt.tiles_n - alt.full_tiles) * alt.splits;
             const double waves_alt = std::ceil(units_alt / double(ctx().sm_count));
-            const double t_pair = double(args.kb_per_split) * (args.kb_per_split >= 32 ? 1650.0 : 2100.0) + (args.splits > 1 ? 18000.0 : 6000.0);
-            const double t_alt = waves_alt * double(alt.kb_per_split) * 1350.0 + (alt.splits > 1 ? 9000.0 : 3000.0);
+            // (k-splits that can meet through distributed shared memory -- one cluster per tile, all resident: at most 74 / 33 / 15
+            // clusters of 2 / 4 / 8 full-SM CTAs on 148 SMs, checked again by launch_tc -- cost about half of the workspace
+            // form's fix-up: 1024^3 on TMEM-A tiles 20.9 -> 17.6 us, 1280^3 on pairs 35.8 -> 31.5, profiles/r02h_cluster_split.log)
+            auto cluster_ok = [](const GemmArgs& g, int cg_) {
+                const int cs = cg_ * g.splits;
+                const unsigned t = g.tiles_m * g.tiles_n;
+                return g.full_tiles == 0 && (g.splits == 2 || g.splits == 4) && (cs == 2 ? t <= 74 : cs == 4 ? t <= 33 : cs == 8 && t <= 15);
+            };
+            const double t_pair = double(args.kb_per_split) * (args.kb_per_split >= 32 ? 1650.0 : 2100.0) +
+                                  (args.splits > 1 ? (cluster_ok(args, 2) ? 16000.0 : 18000.0) : 6000.0);
+            const double t_alt = waves_alt * double(alt.kb_per_split) * 1350.0 + (alt.splits > 1 ? (cluster_ok(alt, 1) ? 4000.0 : 9000.0) : 3000.0);
             if (t_alt < t_pair) {
                 args = alt;
                 ts = true; cg = 1; tn = 128;
@@ -371,6 +380,15 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
             plan_units(args, cg, split3x, batch);
         }
         const unsigned split_tiles = args.tiles_m * args.tiles_n - args.full_tiles;
+        // Every tile split 2 or 4 ways (a product of fewer tiles than half the SMs): the units of a tile form a thread-block
+        // cluster and exchange their partial tiles through distributed shared memory instead of workspace + tickets
+        // (launch_tc falls back to the workspace form when the clusters cannot all be resident).  JZ_GEMM_CLUSTER_SPLIT=0 disables.
+        static const int f_cs = [] {
+            const char* e = std::getenv("JZ_GEMM_CLUSTER_SPLIT");
+            return e && *e ? std::atoi(e) : -1;
+        }();
+        args.cluster_split = (f_cs != 0 && split_tiles && args.full_tiles == 0 && (args.splits == 2 || args.splits == 4) &&
+                              tn / args.splits >= 32 && cg * args.splits <= 8 && batch == 1) ? 1 : 0;
         if (split_tiles) {
             // arrival / departure counters: [0, tiles) and [kTicketSlots/2, ...) of the per-stream ticket block
             // (self-resetting, so no memset sits between two launches and programmatic dependent launch still applies)
@@ -400,7 +418,8 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
                 bb.ptr += size_t(b0) * b.batch_stride;
                 GemmArgs ar = args;
                 ar.C += size_t(b0) * strideC;
-                if (persist) { rc = launch_tc_tf32_persistent(ab, bb, ar, s); continue; }
+                ctx().gemm_last_cluster_split = 0;
+                if (persist) { ar.cluster_split = 0; rc = launch_tc_tf32_persistent(ab, bb, ar, s); continue; }
                 if (ts) { rc = launch_tc_ts(tn, ab, bb, ar, nb, s); continue; }
                 if (split3x) rc = cg == 2 ? launch_tc_cg<MODE_XFORM, 2>(tn, ab, bb, ar, nb, s) : launch_tc_cg<MODE_XFORM, 1>(tn, ab, bb, ar, nb, s);
                 else rc = cg == 2 ? launch_tc_cg<MODE_TF32, 2>(tn, ab, bb, ar, nb, s) : launch_tc_cg<MODE_TF32, 1>(tn, ab, bb, ar, nb, s);
@@ -636,6 +655,7 @@ int jz_gemm_chain_mcast(int transA, int transB, size_t m, size_t n, size_t k, fl
 }
 
 int jz_gemm_last_splits(void) { return ctx().gemm_last_splits; }
+int jz_gemm_last_cluster_split(void) { return ctx().gemm_last_cluster_split; }
 
 }  // extern "C"
 

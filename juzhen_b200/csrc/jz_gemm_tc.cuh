@@ -30,6 +30,10 @@
 //     of the tile are there, and each finishes a 1/splits column slice of the tile: partials summed in split order
 //     (bitwise deterministic whatever the arrival order), alpha/beta/chain, store.  All units of a split tile sit in
 //     consecutive blocks of one launch, so the wait cannot deadlock under in-order block dispatch;
+//   * CLUSTER SPLIT-K (products of fewer tiles than a quarter of the SMs, 2 or 4 splits): the units of a tile are the
+//     CTAs (CTA pairs) of one thread-block cluster; after its mainloop every unit writes the column slices it does not
+//     own straight into the owner's shared memory (st.shared::cluster, the operand stages are idle by then), and the
+//     owner adds the partials in split order -- same bits as the workspace form, without the trip through L2;
 //   * programmatic dependent launch: everything before the first global-memory access (barrier init, TMEM
 //     allocation, tensor-map prefetch) may overlap the tail of the previous kernel in the stream;
 //   * fused all-gather epilogue (multi-GPU): finished elements are also stored to peer images of C, either one
@@ -37,6 +41,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -93,6 +99,8 @@ struct GemmArgs {
     int splits;                 // k-splits per split tile (>= 2 when full_tiles < tiles_m*tiles_n)
     int kb_per_split;           // k-blocks per split unit
     int kb_per_chunk;           // k-blocks accumulated inside TMEM before promotion to registers
+    int cluster_split;          // the `splits` units of a tile form ONE thread-block cluster and exchange their partial tiles
+                                // through distributed shared memory (no workspace, no tickets); needs full_tiles == 0
     float* ws;                  // split-K partial tiles: [split tile][split][rank][TN columns][128 rows]
     unsigned* tickets;          // per-stream self-resetting counters: arrivals at [tile], departures at [kTicketSlots/2 + tile]
     int n_peers;                // additional destinations (peer-GPU images of C, same ldc)
@@ -220,11 +228,11 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 // tcgen05.commit: arrive on `bar` (in every CTA of the pair for CG == 2) when all prior MMAs retire
 template <int CG>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    if constexpr (CG == 2) {
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint16_t pair_mask = 3) {
+    if constexpr (CG == 2) {   // pair_mask: the two CTAs of this pair inside the cluster (3 << even rank)
         asm volatile(
             "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-            "h"((uint16_t)3)
+            "h"(pair_mask)
             : "memory");
     } else {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -331,6 +339,61 @@ __device__ __forceinline__ float tf32_lo_of(float x) {
     return d == d ? __uint_as_float(r) : 0.0f;   // x = inf/nan gives d = nan
 }
 
+// ---- cluster split-K: exchange of partial tiles through distributed shared memory
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// A thread holds row (quarter*32 + lane) x columns [half*TN/2, (half+1)*TN/2) of its unit's partial tile in acc[].  Slice d
+// (columns [d*W, (d+1)*W), W = TN/S) is finished by unit d: every other unit writes its part of that slice into unit d's
+// shared memory at [slot][column of the slice][128 rows], slot = the sender's split index with the owner's skipped.
+template <int CG, int TN, int S>
+__device__ __forceinline__ void cluster_split_send(const float (&acc)[TN / 2], uint32_t recv_base, int split, int half, int row,
+                                                   uint32_t rank) {
+    constexpr int W = TN / S, DPH = (TN / 2) / W;
+    if constexpr (W >= 32 && DPH >= 1) {
+#pragma unroll
+        for (int j = 0; j < DPH; j++) {
+            const int d = half * DPH + j;
+            if (d == split) continue;
+            const uint32_t slot = uint32_t(split < d ? split : split - 1);
+            const uint32_t dst = mapa_shared(recv_base, uint32_t(d) * CG + rank) + ((slot * W) * TILE_M + uint32_t(row)) * 4u;
+#pragma unroll
+            for (int c = 0; c < W; c++) st_cluster_f32(dst + uint32_t(c) * (TILE_M * 4u), acc[j * W + c]);
+        }
+    }
+}
+// The owner's side: partials added in split order (its own from registers at its place in the order), so the sum has
+// the same bits as the workspace form and does not depend on arrival order.
+template <int CG, int TN, int S>
+__device__ __forceinline__ void cluster_split_reduce(float (&acc)[TN / 2], const float* recv, int split, int half, int row) {
+    constexpr int W = TN / S, DPH = (TN / 2) / W;
+    if constexpr (W >= 32 && DPH >= 1) {
+#pragma unroll
+        for (int j = 0; j < DPH; j++) {
+            if (half * DPH + j != split) continue;
+#pragma unroll   // fully: acc[] must keep static indices (registers)
+            for (int c = 0; c < W; c++) {
+                float in[S - 1];
+#pragma unroll
+                for (int t = 0; t < S - 1; t++) in[t] = recv[(size_t(t) * W + c) * TILE_M + row];
+                const float own = acc[j * W + c];
+                float v = split == 0 ? own : in[0];
+#pragma unroll
+                for (int pos = 1; pos < S; pos++) {
+                    const float term = pos < split ? in[pos < S - 1 ? pos : S - 2] : (pos == split ? own : in[pos - 1]);
+                    v = __fadd_rn(v, term);
+                }
+                acc[j * W + c] = v;
+            }
+        }
+    }
+}
+
 // One unit (a whole (CG*128) x TN output tile, or one k-split of it) per CTA group.
 //
 // Barriers (per smem stage): MODE_TF32: TMA of both CTAs -> full (leader) -> MMA -> empty (both).
@@ -378,8 +441,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5;
-    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const uint32_t crank = cluster_ctarank();          // rank in the cluster: pair rank, or split * CG + pair rank (cluster split)
+    const uint32_t rank = CG == 2 ? crank & 1u : 0u;   // rank in the CTA pair
     const bool leader = rank == 0;
+    const bool cs = args.cluster_split != 0;           // uniform over the launch
+    const uint16_t pair_mask = uint16_t(3u << (crank & ~1u));
 
     // unit -> (tile, k range).  Whole tiles first, then the k-splits of the remaining tiles.
     const unsigned unit = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;
@@ -533,6 +599,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        if (cs) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }   // the exchange's two cluster barriers (below)
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader) {
@@ -601,14 +668,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             acc = 1u;
                         }
                     }
-                    umma_commit<CG>(empty_bar(stage));                   // frees this smem stage (both CTAs)
-                    if (chunk_end) umma_commit<CG>(tmem_full_bar(buf));  // chunk accumulator complete
+                    umma_commit<CG>(empty_bar(stage), pair_mask);                   // frees this smem stage (both CTAs)
+                    if (chunk_end) umma_commit<CG>(tmem_full_bar(buf), pair_mask);  // chunk accumulator complete
                 }
                 __syncwarp();
                 if (chunk_end) { chunk++; in_chunk = 0; } else { in_chunk++; }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        if (cs) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }   // the exchange's two cluster barriers (below)
     } else {
         // ===================== epilogue warps: lo-part transform of landed stages (MODE_XFORM), =====================
         // ===================== TMEM chunks -> fp32 registers (RN) -> global                     =====================
@@ -620,8 +688,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int i = 0; i < HALF_N; i++) acc[i] = 0.0f;
         const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * HALF_N);
-        const uint32_t empty0 = tmem_empty_bar(0) & 0xFEFFFFFFu, empty1 = tmem_empty_bar(1) & 0xFEFFFFFFu;
-        const uint32_t ready0 = ready_bar(0) & 0xFEFFFFFFu;  // on the leader CTA
+        // on the leader CTA of the pair (bit 24 of a shared-window address = low bit of the CTA's rank in its cluster); a
+        // single-CTA unit keeps its own barriers -- in a cluster-split launch it has a rank of its own
+        constexpr uint32_t LEADER_MASK = CG == 2 ? 0xFEFFFFFFu : 0xFFFFFFFFu;
+        const uint32_t empty0 = tmem_empty_bar(0) & LEADER_MASK, empty1 = tmem_empty_bar(1) & LEADER_MASK;
+        const uint32_t ready0 = ready_bar(0) & LEADER_MASK;
         // Transform and drain interleave in ONE instruction stream per warp, ordered so that neither can starve
         // the other: k-block j reuses the smem stage of k-block j - STAGES, so it cannot land before the MMAs of
         // k-block j - STAGES have retired; chunk c (k-blocks c*kbc .. (c+1)*kbc - 1) is therefore complete by the
@@ -728,14 +799,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #endif
         float* const Cb = args.C + size_t(bz) * args.strideC;
         const size_t ldc = args.ldc;
-        if (split < 0) {
+        if (cs) {
+            // ---- cluster split-K: the units of this tile are the CTAs (pairs) of this cluster.  Barrier 1: every unit has
+            // left its mainloop (its last chunk is drained, so its MMAs have retired and its operand stages are idle);
+            // then each thread writes the column slices it does not own into the owners' shared memory; barrier 2
+            // (release / acquire at cluster scope) makes them visible; the owner adds the partials in split order and
+            // finishes its slice through the whole-tile path below.
+            const int S = args.splits;
+            const int row_in_cta = quarter * 32 + lane;
+            cluster_sync_all();
+            if (S == 2) cluster_split_send<CG, TN, 2>(acc, smem_base, split, half, row_in_cta, rank);
+            else cluster_split_send<CG, TN, 4>(acc, smem_base, split, half, row_in_cta, rank);
+            cluster_sync_all();
+            const float* const recv = reinterpret_cast<const float*>(gen_base);
+            if (S == 2) cluster_split_reduce<CG, TN, 2>(acc, recv, split, half, row_in_cta);
+            else cluster_split_reduce<CG, TN, 4>(acc, recv, split, half, row_in_cta);
+            if (s_chain.n) epi_bar_sync();   // the program's per-warp scratch (below) overlays the receive area
+        }
+        if (split < 0 || cs) {
             // ---- whole tile: alpha/beta/chain on the register accumulators, coalesced column stores
             const size_t row = size_t(m0) + quarter * 32 + lane;
             const bool row_ok = row < args.m;
             const size_t ncol0 = size_t(n0) + half * HALF_N;
+            const int slice_w = cs ? TILE_N / args.splits : TILE_N;   // cluster split: this unit finishes columns [split*w, (split+1)*w)
 #pragma unroll
             for (int p = 0; p < HALF_N / 32; p++) {
                 const size_t colp = ncol0 + p * 32;
+                if (cs && (half * HALF_N + p * 32) / slice_w != split) continue;   // warp-uniform
                 if (colp < args.n) {  // warp-uniform
                     const int ncols = args.n - colp < 32 ? int(args.n - colp) : 32;
                     float v[32];
@@ -1394,8 +1484,28 @@ static int launch_tc(const Operand& a, const Operand& b, const GemmArgs& args, u
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
+    GemmArgs local = args;
+    if (args.cluster_split) {
+        // the units of a tile as ONE cluster of CG * splits CTAs -- only while every tile's cluster is resident at once (a
+        // cluster of 8 full-SM CTAs needs 8 free SMs of one GPC); otherwise the workspace form, which the caller prepared
+        const unsigned csize = unsigned(CG * args.splits);
+        static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per cluster size; -1 = cannot launch
+        if (csize <= 8 && max_clusters[csize] == 0) {
+            attr[0].val.clusterDim.x = csize;
+            cfg.numAttrs = 1;
+            cfg.gridDim = dim3(csize, 1, 1);
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+            max_clusters[csize] = nc > 0 ? nc : -1;
+            if (std::getenv("JZ_GEMM_DEBUG")) std::fprintf(stderr, "[jz_gemm] CG=%d TN=%d MODE=%d: at most %d resident clusters of %u CTAs\n", CG, TN, MODE, nc, csize);
+            cfg.gridDim = dim3(units * CG, 1, batch);
+        }
+        if (csize <= 8 && args.full_tiles == 0 && int(tiles) <= max_clusters[csize]) attr[0].val.clusterDim.x = csize;
+        else { attr[0].val.clusterDim.x = CG; local.cluster_split = 0; }
+    }
+    ctx().gemm_last_cluster_split = local.cluster_split;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, args);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, local);
     ctx().launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return cuda_fail(e, "gemm_tcgen05_kernel launch");
     return JZ_OK;

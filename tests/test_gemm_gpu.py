@@ -5,6 +5,8 @@ Tolerances (north_star): relative Frobenius error <= 1e-5 in 3xTF32 mode (the de
 oracle's double-accumulated product.  All four op(A), op(B) combinations, ragged tiles,
 odd leading dimensions (the n = 1001 case of tests/testEigen.cu), alpha/beta, fused epilogue.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -232,6 +234,44 @@ def test_gemm_split_k_units(jz, port, mode, shape):
         x = truth / np.float32(1.0 * k)
         want = np.log(np.exp(x) + 1.0)
         assert rel_fro(fused.to_host(), want) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(1024, 1024, 1024, 0, 0, ""), (1024, 1024, 1024, 1, 1, ""), (1024, 1024, 1024, 0, 0, "JZ_GEMM_TS=0"),
+                                   (1024, 1024, 1024, 1, 0, "JZ_GEMM_TS=0"), (1000, 1100, 900, 0, 1, ""), (1000, 1100, 900, 0, 1, "JZ_GEMM_TS=0"),
+                                   (1280, 2048, 768, 0, 0, ""), (8192, 8192, 32, 0, 0, ""), (8192, 4100, 40, 1, 0, ""),
+                                   (1536, 1536, 1536, 0, 0, "JZ_GEMM_TS=0"), (1024, 60000, 784, 0, 1, "")])
+def test_gemm_cluster_split_same_bits_as_workspace_form(shape, tmp_path):
+    """Products of few tiles split every tile along k; the units of a tile then form one thread-block cluster and exchange
+    their partial tiles through distributed shared memory (jz_gemm_tc.cuh, cluster_split_send / _reduce): clusters of 2
+    single CTAs (TMEM-A tiles), of 2 CTA pairs, of 4 CTA pairs.  The partials are added in split order either way, so the
+    result must have the SAME BITS as the workspace + ticket form (JZ_GEMM_CLUSTER_SPLIT=0, read once per process: both
+    runs are fresh processes), with alpha / beta and with a fused program."""
+    import subprocess
+    import sys
+    m, k, n, ta, tb, extra = shape
+    extra_env = dict(kv.split("=") for kv in extra.split()) if extra else {}
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = {}
+    for name, env in (("cluster", extra_env), ("workspace", {**extra_env, "JZ_GEMM_CLUSTER_SPLIT": "0"})):
+        out = str(tmp_path / f"{name}.npz")
+        r = subprocess.run([sys.executable, os.path.join(here, "_gemm_dump.py"), *map(str, (m, k, n, ta, tb, 0, 7)), out],
+                           env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[name] = np.load(out)
+    assert int(res["workspace"]["cluster_split"]) == 0
+    assert int(res["workspace"]["splits"]) > 1, "the shape is meant to split along k"
+    print(f"cluster split {shape}: splits={int(res['cluster']['splits'])} cluster_form={int(res['cluster']['cluster_split'])}")
+    if (m, k, n) in ((1024, 1024, 1024), (8192, 8192, 32)) and not extra:   # (16 clusters of 8 full-SM CTAs are not all resident on 148 SMs)
+        assert int(res["cluster"]["cluster_split"]) == 1, ("expected the cluster form", shape, int(res["cluster"]["splits"]))
+    for key in ("axpby", "chain"):
+        assert np.array_equal(bits(res["cluster"][key]), bits(res["workspace"][key])), (shape, key)
+    rng = np.random.default_rng(7)
+    P = rng.standard_normal((k, m) if ta else (m, k)).astype(np.float32)
+    Q = rng.standard_normal((n, k) if tb else (k, n)).astype(np.float32)
+    C0 = rng.standard_normal((m, n)).astype(np.float32)
+    if m * n * k <= 1 << 32:
+        truth = (P.T if ta else P).astype(np.float64) @ (Q.T if tb else Q).astype(np.float64)
+        assert rel_fro(res["cluster"]["axpby"], 0.75 * truth - 0.5 * C0) < 1e-5
 
 
 @pytest.mark.parametrize("shape", [(8192, 1024, 32), (4096, 520, 48), (2048, 777, 64), (128, 4096, 1024), (100, 3000, 300),
