@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("JZ_REFERENCE", "/root/reference")
 OUT = os.path.join(ROOT, "build", "dropin")
 STAGE, OBJ, BIN, PROJECT = (os.path.join(OUT, d) for d in ("stage", "obj", "bin", "project"))
+LIBDIR = os.path.join(OUT, "lib")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 PYSITE = "/opt/prime-rl/.venv/lib/python3.12/site-packages"
 
@@ -57,6 +58,9 @@ OWN_TESTS = [("test_fusion", "test_fusion.cu", []), ("bench_attention", "bench_a
              ("bench_overhead", "bench_overhead.cu", []), ("bench_mnist_step", "bench_mnist_step.cu", [])]
 # own main(): linked without launcher.o
 OWN_MAIN = [("test_mg_dot", "test_mg_dot.cu", [])]
+# test infrastructure as a shared library (own entry points, no main): the flat C wrapper over the C++ shell that
+# tests/test_shell_gpu.py drives through ctypes
+OWN_LIBS = [("libjz_shell_capi.so", "shell_capi.cu", [])]
 OURS_IN_CPP = {"cumatrix.cuh", "memory.hpp", "jz_lazy.hpp", "jz_mg.hpp"}
 REF_CPP = ["core.hpp", "matrix.hpp", "operators.hpp", "helper.hpp", "juzhen.hpp", "cpulinalg.hpp"]
 
@@ -84,7 +88,7 @@ def stage():
         for p in glob.glob(os.path.join(REF, sub, "*")):
             if os.path.isfile(p):
                 link(p, os.path.join(STAGE, sub, os.path.basename(p)))
-    for _, src, _x in OWN_TESTS + OWN_MAIN:
+    for _, src, _x in OWN_TESTS + OWN_MAIN + OWN_LIBS:
         link(os.path.join(HERE, "tests", src), os.path.join(STAGE, "tests", src))
     link(os.path.join(REF, "external", "xpu_info", "xpu_info.hpp"), os.path.join(STAGE, "external", "xpu_info", "xpu_info.hpp"))
     eig = os.path.join(REF, "external", "Eigen3")
@@ -136,7 +140,7 @@ def build(only=None, force=False):
         print(f"build_dropin: {REF} absent -- keeping prebuilt binaries under {BIN} if any")
         return []
     stage()
-    for d in (OBJ, BIN):
+    for d in (OBJ, BIN, LIBDIR):
         os.makedirs(d, exist_ok=True)
     fl, ob = flags()
     ours = [os.path.join(HERE, f) for f in ("cumatrix.cuh", "cumatrix.cu", "memory.hpp", "launcher.cu", "jz_lazy.hpp", "jz_mg.hpp")] + \
@@ -159,6 +163,13 @@ def build(only=None, force=False):
 
     def one(prog):
         name, src, extra = prog
+        if name.endswith(".so"):   # shared library: its own translation unit + a position-independent cumatrix.cu
+            lib = os.path.join(LIBDIR, name)
+            if not force and newer(lib, ours + [os.path.realpath(os.path.join(STAGE, src))]):
+                return name, "up to date"
+            run([NVCC, *fl, *extra, "-Xcompiler", "-fPIC", "-shared", os.path.join(STAGE, src), os.path.join(STAGE, "cpp", "cumatrix.cu"),
+                 *link_flags, "-o", lib], f"build {name}")
+            return name, "built"
         exe = os.path.join(BIN, name)
         if not force and newer(exe, ours + objs + [os.path.realpath(os.path.join(STAGE, src))]):
             return name, "up to date"
@@ -168,7 +179,7 @@ def build(only=None, force=False):
         run([NVCC, *fl, *extra, os.path.join(STAGE, src), *use, *link_flags, "-o", exe], f"build {name}")
         return name, "built"
 
-    todo = [p for p in PROGRAMS + [(n, "tests/" + s, x) for n, s, x in OWN_TESTS + OWN_MAIN] if not only or p[0] in only]
+    todo = [p for p in PROGRAMS + [(n, "tests/" + s, x) for n, s, x in OWN_TESTS + OWN_MAIN + OWN_LIBS] if not only or p[0] in only]
     with concurrent.futures.ThreadPoolExecutor(max_workers=6) as ex:
         res = list(ex.map(one, todo))
     for name, st in res:

@@ -572,7 +572,11 @@ void Matrix<CUDAfloat>::slice(size_t rstart, size_t rend, size_t cstart, size_t 
     if (transpose) { std::swap(rstart, cstart); std::swap(rend, cend); }
     const size_t r = rend - rstart, c = cend - cstart;
     const float* from = M.dev();
-    JZ_DO(jz_copy2d(wdev() + cstart * numrow + rstart, numrow, from, r ? r : 1, r, c, 0, S()));
+    // Assignment in LOGICAL coordinates, the CPU oracle's semantics (cpp/core.hpp:365-373: elem(i, j) on both sides).  The
+    // reference's GPU copyKernel reads M's physical buffer whatever M's flag (cpp/cumatrix.cuh:208-222), which is the same
+    // thing whenever the two flags agree; when they differ the block is M's physical buffer transposed.
+    const bool mixed = M.transpose != transpose;
+    JZ_DO(jz_copy2d(wdev() + cstart * numrow + rstart, numrow, from, M.numrow ? M.numrow : 1, r, c, mixed ? 1 : 0, S()));
 }
 
 void copy(Matrix<CUDAfloat>& dest, const Matrix<CUDAfloat>& src) {  // cpp/cukernels.cu:241-256: dest is re-allocated
