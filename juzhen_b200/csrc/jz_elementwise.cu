@@ -63,6 +63,8 @@ __device__ __forceinline__ void apply_tile(const F& f, float (&x)[N]) {
 }
 template <int N>
 __device__ __forceinline__ void apply_tile(const UnaryF<JZ_LOG>&, float (&x)[N]) { log_tile<N>(x); }
+template <int N>
+__device__ __forceinline__ void apply_tile(const UnaryF<JZ_DTANH>&, float (&x)[N]) { dtanh_tile<N>(x); }
 
 template <class F>
 __global__ void __launch_bounds__(kThreads) map1_v4(float* out, const float* in, size_t n, F f) {
@@ -192,26 +194,34 @@ __global__ void __launch_bounds__(kThreads) chain_v4(float* out, const float* in
     pdl_enter();
     __shared__ ChainParams c;
     stage_chain(&c, cp, threadIdx.x);
-    __syncthreads();
     const size_t n4 = n >> 2;
     const float4* in4 = reinterpret_cast<const float4*>(in);
     float4* out4 = reinterpret_cast<float4*>(out);
     const size_t tile = size_t(kThreads) * kUnroll;
-    for (size_t base = size_t(blockIdx.x) * tile; base < n4; base += size_t(gridDim.x) * tile) {
-        float v[kUnroll * 4];
+    // one tile per CTA as a rule: its loads are issued BEFORE the barrier that publishes the staged parameters, so the
+    // staging (one thread, ~100 bytes) costs no memory latency
+    size_t base = size_t(blockIdx.x) * tile;
+    float v[kUnroll * 4];
+    auto load_tile = [&](size_t b) {
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
-            const size_t i = base + size_t(u) * kThreads + threadIdx.x;
+            const size_t i = b + size_t(u) * kThreads + threadIdx.x;
             float4 t = make_float4(1.f, 1.f, 1.f, 1.f);
             if (i < n4) t = in4[i];
             v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
         }
+    };
+    if (base < n4) load_tile(base);
+    __syncthreads();
+    while (base < n4) {
         apply_chain<kUnroll * 4>(v, c);
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
             const size_t i = base + size_t(u) * kThreads + threadIdx.x;
             if (i < n4) out4[i] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
         }
+        base += size_t(gridDim.x) * tile;
+        if (base < n4) load_tile(base);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const size_t i = (n4 << 2) + threadIdx.x;

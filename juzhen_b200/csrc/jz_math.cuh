@@ -68,6 +68,61 @@ __device__ __forceinline__ float dtanh_acc(float x) {
     return __fmaf_rn(-q, __fmul_rn(c, rc), q);
 }
 
+// The same computation on two elements per instruction (packed fp32 pipe forms, see log_main2 below): every lane goes
+// through the same sequence of individually rounded operations as dtanh_acc, so the bits are the same; 25 of its ~30
+// instructions are floating-point and pack.  Both lanes must be in the main range (|x| <= 40).
+__device__ __forceinline__ float2 jz_splat2(float c) { return make_float2(c, c); }
+__device__ __forceinline__ float2 jz_neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 exp_neg_1ulp2(float2 t) {
+    const float2 z = __ffma2_rn(t, jz_splat2(1.4426950408889634f), jz_splat2(12582912.0f));
+    const float2 n = __fadd2_rn(z, jz_splat2(-12582912.0f));
+    float2 r = __ffma2_rn(n, jz_splat2(-0.693145751953125f), t);
+    r = __ffma2_rn(n, jz_splat2(-1.4286068203094173e-06f), r);
+    float2 p = jz_splat2(0.00019899278413504362f);
+    p = __ffma2_rn(p, r, jz_splat2(0.0013933645095676184f));
+    p = __ffma2_rn(p, r, jz_splat2(0.0083332983776927f));
+    p = __ffma2_rn(p, r, jz_splat2(0.04166646674275398f));
+    p = __ffma2_rn(p, r, jz_splat2(0.1666666716337204f));
+    p = __ffma2_rn(p, r, jz_splat2(0.5f));
+    p = __ffma2_rn(p, __fmul2_rn(r, r), r);
+    p = __fadd2_rn(jz_splat2(1.0f), p);
+    return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(z.x) << 23)),
+                       __int_as_float(__float_as_int(p.y) + (__float_as_int(z.y) << 23)));
+}
+__device__ __forceinline__ float2 dtanh_acc2(float2 x) {   // |x.x|, |x.y| <= 40
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 e = exp_neg_1ulp2(make_float2(-2.0f * ax.x, -2.0f * ax.y));
+    const float2 s = __fadd2_rn(jz_splat2(1.0f), e);
+    const float2 serr = __fadd2_rn(e, jz_neg2(__fadd2_rn(s, jz_splat2(-1.0f))));
+    const float2 t = __fmul2_rn(s, s);
+    const float2 terr = __ffma2_rn(s, s, jz_neg2(t));
+    const float2 c = __ffma2_rn(make_float2(2.0f * s.x, 2.0f * s.y), serr, terr);
+    const float2 num = make_float2(4.0f * e.x, 4.0f * e.y);
+    float2 rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc.x) : "f"(t.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc.y) : "f"(t.y));
+    const float2 q0 = __fmul2_rn(num, rc);
+    const float2 q = __ffma2_rn(__ffma2_rn(jz_neg2(q0), t, num), rc, q0);
+    return __ffma2_rn(jz_neg2(q), __fmul2_rn(c, rc), q);
+}
+template <int N>
+__device__ __forceinline__ void dtanh_tile(float (&v)[N]) {
+    bool main_range = (N % 2) == 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) main_range &= fabsf(v[i]) <= 40.0f;   // false for NaN too
+    if (main_range) {
+#pragma unroll
+        for (int i = 0; i + 1 < N; i += 2) {
+            const float2 r = dtanh_acc2(make_float2(v[i], v[i + 1]));
+            v[i] = r.x;
+            v[i + 1] = r.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = dtanh_acc(v[i]);
+    }
+}
+
 // log(x) in ~20 instructions on the main path (CUDA's logf is ~28 and makes the fused softplus chain
 // ALU-bound): x = m * 2^e with m in [2/3, 4/3), f = m - 1 (exact),
 // log1p(f) = f + f^2 * (-1/2 + f * Q7(f)), result = fma(e, ln2, log1p(f)).  Measured worst case 0.92 ulp from the
@@ -93,6 +148,29 @@ __device__ __forceinline__ float log_main(float x) {  // positive normal x only
     return __fmaf_rn(float(e), 0.6931471805599453f, r);
 }
 __device__ __forceinline__ float log_1ulp(float x) { return log_needs_library(x) ? logf(x) : log_main(x); }
+// Two elements per instruction: sm_100's packed fp32 pipe forms (FFMA2 / FADD2 / FMUL2 = fma / add / mul .rn.f32x2, each
+// lane rounded exactly like the scalar instruction, so the result has the same bits as log_main on either lane).  The
+// fused chain is ISSUE-bound (~38 instructions per element against 8 bytes, ncu: sm 84 %, dram 61-68 %); the thirteen
+// floating-point instructions of the polynomial become 6.5 per element.  Only fma-into-fma sequences are packed:
+// ptxas contracts a mul.rn.f32x2 followed by an add.rn.f32x2 into one FFMA2 (seen in SASS), which would break the
+// separately rounded `s1*x + a` of the affine steps -- those stay scalar (__fmul_rn / __fadd_rn are never contracted).
+__device__ __forceinline__ float2 splat2(float c) { return make_float2(c, c); }
+__device__ __forceinline__ float2 log_main2(float2 x) {  // positive normal x only, both lanes
+    const int ix0 = __float_as_int(x.x), ix1 = __float_as_int(x.y);
+    const int e0 = (ix0 - 0x3f2aaaab) >> 23, e1 = (ix1 - 0x3f2aaaab) >> 23;
+    const float2 f = __fadd2_rn(make_float2(__int_as_float(ix0 - (e0 << 23)), __int_as_float(ix1 - (e1 << 23))), splat2(-1.0f));
+    float2 q = splat2(-0.128597691655159f);
+    q = __ffma2_rn(q, f, splat2(0.1401381939649582f));
+    q = __ffma2_rn(q, f, splat2(-0.12192238867282867f));
+    q = __ffma2_rn(q, f, splat2(0.13999086618423462f));
+    q = __ffma2_rn(q, f, splat2(-0.16679848730564117f));
+    q = __ffma2_rn(q, f, splat2(0.20010896027088165f));
+    q = __ffma2_rn(q, f, splat2(-0.24999813735485077f));
+    q = __ffma2_rn(q, f, splat2(0.3333320617675781f));
+    const float2 w = __ffma2_rn(f, q, splat2(-0.5f));
+    const float2 r = __ffma2_rn(__fmul2_rn(f, f), w, f);
+    return __ffma2_rn(make_float2(float(e0), float(e1)), splat2(0.6931471805599453f), r);
+}
 // register-tile form: ONE branch per tile instead of one per element (the per-element form costs ~8 extra
 // instructions per element in branch bookkeeping, measured in the fused chain)
 template <int N>
@@ -101,8 +179,17 @@ __device__ __forceinline__ void log_tile(float (&v)[N]) {
 #pragma unroll
     for (int i = 0; i < N; i++) special |= log_needs_library(v[i]);
     if (!special) {
+        if constexpr (N % 2 == 0) {
 #pragma unroll
-        for (int i = 0; i < N; i++) v[i] = log_main(v[i]);
+            for (int i = 0; i < N; i += 2) {
+                const float2 r = log_main2(make_float2(v[i], v[i + 1]));
+                v[i] = r.x;
+                v[i + 1] = r.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = log_main(v[i]);
+        }
     } else {   // rare: decide per element, so that the result of an element never depends on its tile mates
 #pragma unroll  // (a rolled loop would index v[] dynamically and push the whole tile into local memory)
         for (int i = 0; i < N; i++) v[i] = log_1ulp(v[i]);
@@ -140,15 +227,31 @@ __device__ __forceinline__ void apply_step(float (&v)[N], int kind, float s1, fl
             }
             break;
         JZ_CASE(JZ_TANH)
-        JZ_CASE(JZ_DTANH)
+        case JZ_DTANH:
+            if constexpr (N <= 16) {
+                dtanh_tile<N>(v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; i++) v[i] = dtanh_acc(v[i]);
+            }
+            break;
         JZ_CASE(JZ_SQUARE)
         JZ_CASE(JZ_SQRT)
         JZ_CASE(JZ_RELU)
         JZ_CASE(JZ_DRELU)
 #undef JZ_CASE
         case JZ_STEP_AFFINE:
+            if (s1 == 1.0f && N % 2 == 0) {   // x + a: 1 * x is exact, so only the addition rounds -- two lanes per FADD2
 #pragma unroll
-            for (int i = 0; i < N; i++) v[i] = affine_rn(v[i], s1, a);
+                for (int i = 0; i + 1 < N; i += 2) {
+                    const float2 r = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(a, a));
+                    v[i] = r.x;
+                    v[i + 1] = r.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; i++) v[i] = affine_rn(v[i], s1, a);
+            }
             break;
         case JZ_STEP_ELEMINV:
 #pragma unroll

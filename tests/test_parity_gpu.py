@@ -155,6 +155,38 @@ def test_ragged_sizes_and_unaligned_views(jz, port, n):
             assert np.max(ulp_dist(out.to_host().ravel()[off:off + n], port.unary("exp", x[off:off + n]))) <= 2
 
 
+def test_packed_fp32_tile_paths_have_the_bits_of_the_scalar_paths(jz):
+    """The vector kernels evaluate log, d_tanh and the `x + a` steps of a chain two elements per instruction (sm_100's
+    FFMA2 / FADD2 / FMUL2, jz_math.cuh: log_main2, dtanh_acc2); a 4-byte-misaligned view of the same data takes the scalar
+    kernels (map1_s, chain_s).  Every lane of a packed instruction rounds like the scalar instruction, so the two paths
+    must agree BIT FOR BIT -- over every binade, the special values, and both sides of the d_tanh range switch."""
+    rng = np.random.default_rng(2024)
+    n = 1 << 20
+    mags = np.exp2(rng.uniform(-126, 127, n)).astype(np.float32)
+    x = (mags * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+    x[:16] = [0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 40.0, -40.0, 40.000004, 39.999996, 1e-45, -1e-45, 88.0, -88.0, 3.4e38]
+    small = (rng.standard_normal(n) * 4).astype(np.float32)
+    L = jz.lib()
+    for name, data in (("wide", x), ("activations", small), ("positive", np.abs(x))):
+        src = np.concatenate([np.zeros(1, np.float32), data])     # element 1.. = the same values at a 4-byte-misaligned address
+        d_al, d_mis = flat(jz, data), flat(jz, src)
+        for op in ("log", "dtanh", "exp", "tanh"):
+            o_al, o_mis = jz.CM.empty("a", n, 1), jz.CM.empty("m", n + 1, 1)
+            jz._lib.check(L.jz_unary(jz._lib.UNARY[op], o_al.ptr, d_al.ptr, n, None))
+            jz._lib.check(L.jz_unary(jz._lib.UNARY[op], o_mis.ptr + 4, d_mis.ptr + 4, n, None))
+            a, m = o_al.to_host().ravel(), o_mis.to_host().ravel()[1:]
+            both_nan = np.isnan(a) & np.isnan(m)
+            assert np.array_equal(bits(a)[~both_nan], bits(m)[~both_nan]), (name, op, int(np.sum(bits(a) != bits(m))))
+        steps = [("exp",), ("affine", 1.0, 1.0), ("log",), ("affine", float(np.float32(0.2)), 0.0), ("dtanh",), ("affine", 1.0, -0.25)]
+        arr, ns = jz._lib.make_steps(steps)
+        o_al, o_mis = jz.CM.empty("a", n, 1), jz.CM.empty("m", n + 1, 1)
+        jz._lib.check(L.jz_chain(o_al.ptr, d_al.ptr, n, arr, ns, None))
+        jz._lib.check(L.jz_chain(o_mis.ptr + 4, d_mis.ptr + 4, n, arr, ns, None))
+        a, m = o_al.to_host().ravel(), o_mis.to_host().ravel()[1:]
+        both_nan = np.isnan(a) & np.isnan(m)
+        assert np.array_equal(bits(a)[~both_nan], bits(m)[~both_nan]), (name, "chain")
+
+
 # ------------------------------------------------------------------ reductions
 @pytest.mark.parametrize("name", ["r1", "r2", "r3", "r4"])
 def test_reductions_vs_reference_fixture(jz, golden, name):
