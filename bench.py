@@ -307,6 +307,12 @@ def run_ours(args):
                         if rc:
                             raise RuntimeError(L.jz_last_error().decode())
                     key = f"{mode_name}_{gn}{suffix}"
+                    if gn >= 8192:
+                        # launches of milliseconds leave the part power-capped: without a pause the configurations timed
+                        # later in the list inherit a lower SM clock (8192^3 3xTF32: 293-295 TFLOP/s for every layout when each
+                        # starts from idle, 243-253 for whichever comes second and third, profiles/r02h_layout_order_8192.log)
+                        torch.cuda.synchronize()
+                        time.sleep(1.5)
                     try:
                         ms, _ = timed(g, reps, 3)
                     except RuntimeError as e:

@@ -1,7 +1,9 @@
 """SASS evidence for profiles/: per kernel of libjz_b200.so, how many tcgen05 MMAs (UTC*MMA), TMEM loads (LDTM), TMA
 loads (UTMALDG), bulk / async copies (UBLKCP, LDGSTS), system-scope stores (ST.SYS = STG.E.STRONG.SYS: what
 multimem.st.relaxed.sys to an NVSwitch multicast address and the st.release.sys of the cross-GPU barrier compile to --
-SASS has no separate mnemonic for a multicast store, the address decides), 128-bit global accesses (LDG.E.128 / STG.E.128) and legacy tensor instructions (HMMA: must be zero) appear.
+SASS has no separate mnemonic for a multicast store, the address decides), 128-bit global accesses (LDG.E.128 / STG.E.128), packed two-lane fp32 instructions (F*2 = FFMA2 / FADD2 / FMUL2), stores into another
+CTA's shared memory (ST.E = generic stores: the st.shared::cluster of the cluster split-K exchange compile to these -- a mapa'd shared-window
+address goes through the generic path -- as do the epilogue's stores through peer pointers), cluster barriers (UCGABAR = barrier.cluster arrive / wait) and legacy tensor instructions (HMMA: must be zero) appear.
     python scripts/sass_summary.py > profiles/sass_summary.txt      (build container: cuobjdump, no GPU needed)"""
 import collections
 import os
@@ -15,7 +17,8 @@ out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
 pats = collections.OrderedDict([
     ("UTC*MMA", r"\bUTC[A-Z]*MMA"), ("LDTM", r"\bLDTM"), ("UTMALDG", r"\bUTMALDG"), ("UBLKCP", r"\bUBLKCP"),
     ("LDGSTS", r"\bLDGSTS"), ("ST.SYS", r"\bSTG\.E\.STRONG\.SYS"), ("LDG.128", r"\bLDG\.E\.[A-Z.]*128"),
-    ("STG.128", r"\bSTG\.E\.[A-Z.]*128"), ("SYNCS", r"\bSYNCS"), ("HMMA", r"\bHMMA"), ("instr", r"^\s*/\*[0-9a-f]{4,}\*/"),
+    ("STG.128", r"\bSTG\.E\.[A-Z.]*128"), ("SYNCS", r"\bSYNCS"), ("F*2", r"\bF(FMA|ADD|MUL)2\b"), ("ST.E", r"\bST\.E\b"),
+    ("UCGABAR", r"\bUCGABAR"), ("HMMA", r"\bHMMA"), ("instr", r"^\s*/\*[0-9a-f]{4,}\*/"),
 ])
 kern = None
 counts = collections.OrderedDict()
