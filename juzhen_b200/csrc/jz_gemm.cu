@@ -325,6 +325,8 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         args.chain = chain;
         args.ws = nullptr;
         args.tickets = nullptr;
+        args.walk_units = 0;
+        args.cluster_split = 0;
 #ifdef JZ_GEMM_PROFILE
         args.prof = prof_buf();
 #endif
@@ -410,9 +412,21 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         // 16384^3: 602 -> 545 TFLOP/s, A.T*B 552 -> 432; at 4096^3 689 -> 729, profiles/r02d_gemm_tf32_persistent_ab.log)
         const bool fits_l2_wave = (double(m) + double(n)) * double(k) * 4.0 <= 540e6;
         const bool persist = persist_ok && (f_persist == 1 || (f_persist != 0 && fits_l2_wave && n_units > unsigned(ctx().sm_count) / 2));
+        // A strided batch with more (member, tile) units than SMs (attention: hundreds to thousands of members of a few
+        // k-blocks each): one CTA group per SM (pair) walks the units, so barrier / tensor-memory set-up is paid once per
+        // SM and the producer loads the next unit's operands while the current one is stored.  No program in the epilogue
+        // then (its scratch would overlay live operand stages).  JZ_GEMM_WALK=0 disables.
+        static const bool no_walk = [] { const char* e = std::getenv("JZ_GEMM_WALK"); return e && e[0] == '0'; }();
+        const unsigned long long units_all = (unsigned long long)(args.tiles_m) * args.tiles_n * batch;
+        const bool walkable = ts || !split3x || cg == 2;   // the variants instantiated with the walk (not the shared-memory 3xTF32 form on single CTAs)
+        const bool walk = !no_walk && walkable && batch > 1 && !persist && chain.n == 0 && !chain.bias && n_peers == 0 && !mc &&
+                          units_all > (unsigned long long)(ctx().sm_count / cg) && units_all < (1ull << 31);
+        if (walk) args.walk_units = unsigned(units_all);
         if (rc == JZ_OK) {
-            for (unsigned b0 = 0; b0 < batch && rc == JZ_OK; b0 += 65535u) {   // grid.z limit
-                const unsigned nb = batch - b0 < 65535u ? batch - b0 : 65535u;
+            const unsigned zcap = walk ? 0xFFFFFFFFu : 65535u;   // grid.z limit (a walk has no grid.z)
+            for (unsigned long long b0l = 0; b0l < batch && rc == JZ_OK; b0l += zcap) {
+                const unsigned b0 = unsigned(b0l);
+                const unsigned nb = batch - b0 < zcap ? batch - b0 : zcap;
                 Operand ab = a, bb = b;
                 ab.ptr += size_t(b0) * a.batch_stride;
                 bb.ptr += size_t(b0) * b.batch_stride;

@@ -34,6 +34,10 @@
 //     CTAs (CTA pairs) of one thread-block cluster; after its mainloop every unit writes the column slices it does not
 //     own straight into the owner's shared memory (st.shared::cluster, the operand stages are idle by then), and the
 //     owner adds the partials in split order -- same bits as the workspace form, without the trip through L2;
+//   * WALKED BATCHES (strided batches with more (member, tile) units than SMs): a CTA keeps its barriers, its tensor-memory
+//     allocation and its TMA pipeline and walks the units u, u + P, u + 2P ...: the producer runs ahead into the next unit's
+//     operands while the epilogue warps store the current one, and the per-CTA prologue (a large part of a unit of 4 k-blocks)
+//     is paid once per SM instead of once per unit;
 //   * programmatic dependent launch: everything before the first global-memory access (barrier init, TMEM
 //     allocation, tensor-map prefetch) may overlap the tail of the previous kernel in the stream;
 //   * fused all-gather epilogue (multi-GPU): finished elements are also stored to peer images of C, either one
@@ -99,6 +103,9 @@ struct GemmArgs {
     int splits;                 // k-splits per split tile (>= 2 when full_tiles < tiles_m*tiles_n)
     int kb_per_split;           // k-blocks per split unit
     int kb_per_chunk;           // k-blocks accumulated inside TMEM before promotion to registers
+    unsigned walk_units;        // strided batches of many small members: a CTA (pair) WALKS the (member, tile) units u, u + P,
+                                // u + 2P ... (P = CTA groups in the grid) instead of exiting after one -- barriers, tensor
+                                // memory and the TMA pipeline live across units (0: one unit per CTA group)
     int cluster_split;          // the `splits` units of a tile form ONE thread-block cluster and exchange their partial tiles
                                 // through distributed shared memory (no workspace, no tickets); needs full_tiles == 0
     float* ws;                  // split-K partial tiles: [split tile][split][rank][TN columns][128 rows]
@@ -398,7 +405,7 @@ __device__ __forceinline__ void cluster_split_reduce(float (&acc)[TN / 2], const
 //
 // Barriers (per smem stage): MODE_TF32: TMA of both CTAs -> full (leader) -> MMA -> empty (both).
 // MODE_XFORM: TMA -> full (own CTA) -> epilogue warps write lo -> ready (leader) -> MMA -> empty (both).
-template <int CG, int MODE, int TN, bool AMN, bool BMN>
+template <int CG, int MODE, int TN, bool AMN, bool BMN, bool WALK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
     constexpr bool TS = MODE == MODE_XFORM_TS;       // A operand (hi, lo) staged in tensor memory
@@ -449,12 +456,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     // unit -> (tile, k range).  Whole tiles first, then the k-splits of the remaining tiles.
     const unsigned unit = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;
-    const int bz = int(blockIdx.z);
+    const unsigned walk = WALK ? args.walk_units : 0u;           // > 0: this CTA group walks units unit, unit + ustride, ...
+                                                                 // (a compile-time variant: the one-unit kernels keep their registers)
+    const unsigned ustride = (CG == 2 ? gridDim.x >> 1 : gridDim.x);
     const int num_kb_total = int((args.k + BK - 1) / BK);
     unsigned tile = unit;
     int kb0 = 0, num_kb = num_kb_total, split = -1;
     unsigned split_tile = 0;
-    if (unit >= args.full_tiles) {
+    if (!walk && unit >= args.full_tiles) {
         const unsigned r = unit - args.full_tiles;
         split_tile = r / unsigned(args.splits);
         split = int(r % unsigned(args.splits));
@@ -462,17 +471,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         kb0 = split * args.kb_per_split;
         num_kb = num_kb_total - kb0 < args.kb_per_split ? num_kb_total - kb0 : args.kb_per_split;
     }
-    // tile coordinates (grouped rasterisation for L2 reuse of the A / B panels)
-    constexpr unsigned GROUP = 8;
-    const unsigned per_group = GROUP * args.tiles_n;
-    const unsigned group_id = tile / per_group;
-    const unsigned first_m = group_id * GROUP;
-    const unsigned group_m = args.tiles_m - first_m < GROUP ? args.tiles_m - first_m : GROUP;
-    const unsigned tm = first_m + (tile % per_group) % group_m;
-    const unsigned tn = (tile % per_group) / group_m;
-    const int m0 = int(tm) * (CG * TILE_M) + int(rank) * TILE_M;  // first row of this CTA
-    const int n0 = int(tn) * TILE_N;
-    const int nb0 = n0 + (CG == 2 ? int(rank) * (TILE_N / 2) : 0);         // first B row (= C column) this CTA loads
+    // tile coordinates (grouped rasterisation for L2 reuse of the A / B panels); a walked unit u is tile u % tiles of
+    // member u / tiles.  Every warp role keeps its own copy and re-places it per unit.
+    struct Place { int m0, n0, nb0, bz; };
+    auto place = [&](unsigned u) -> Place {
+        unsigned t = u;
+        int z = int(blockIdx.z);
+        if (walk) {
+            const unsigned tiles = args.tiles_m * args.tiles_n;
+            z = int(u / tiles);
+            t = u % tiles;
+        }
+        constexpr unsigned GROUP = 8;
+        const unsigned per_group = GROUP * args.tiles_n;
+        const unsigned group_id = t / per_group;
+        const unsigned first_m = group_id * GROUP;
+        const unsigned group_m = args.tiles_m - first_m < GROUP ? args.tiles_m - first_m : GROUP;
+        const unsigned tm = first_m + (t % per_group) % group_m;
+        const unsigned tn = (t % per_group) / group_m;
+        const int n0_ = int(tn) * TILE_N;
+        return Place{int(tm) * (CG * TILE_M) + int(rank) * TILE_M,                 // first row of this CTA
+                     n0_, n0_ + (CG == 2 ? int(rank) * (TILE_N / 2) : 0), z};       // first B row (= C column) this CTA loads
+    };
+    const Place first_place = place(walk ? unit : tile);
     const int kbc = args.kb_per_chunk;
     const int num_chunks = (num_kb + kbc - 1) / kbc;
 
@@ -580,6 +601,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #ifdef JZ_GEMM_PROFILE
             long long pf_wait = 0, pf_t0 = clock64();
 #endif
+            Place pl = first_place;
+            for (unsigned u = unit;;) {
             for (int kb = 0; kb < num_kb; kb++) {
 #ifdef JZ_GEMM_PROFILE
                 const long long pf_a = clock64();
@@ -594,9 +617,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 else if (leader) mbar_arrive_expect_tx(full_bar(stage), uint32_t(STAGE_BYTES) * CG);
                 const uint32_t sa = smem_base + stage * STAGE_BYTES;
                 const int kc = (kb0 + kb) * BK;
-                tma_load_tile<AMN, TILE_M, TO_LEADER>(sa, &tmA, full_bar(stage), kc, m0, bz);
-                tma_load_tile<BMN, B_ROWS, TO_LEADER>(sa + A_BYTES, &tmB, full_bar(stage), kc, nb0, bz);
+                tma_load_tile<AMN, TILE_M, TO_LEADER>(sa, &tmA, full_bar(stage), kc, pl.m0, pl.bz);
+                tma_load_tile<BMN, B_ROWS, TO_LEADER>(sa + A_BYTES, &tmB, full_bar(stage), kc, pl.nb0, pl.bz);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (!walk || (u += ustride) >= walk) break;
+            pl = place(u);   // next unit of the walk: the pipeline simply continues into its operands
             }
         }
         if (cs) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }   // the exchange's two cluster barriers (below)
@@ -608,6 +634,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #ifdef JZ_GEMM_PROFILE
             long long pf_ready = 0, pf_tmem = 0, pf_t0 = clock64();
 #endif
+            for (unsigned u = unit;;) {   // (chunk counts on across the units of a walk: the two TMEM buffers keep alternating)
             for (int kb = 0; kb < num_kb; kb++) {
                 const uint32_t buf = uint32_t(chunk) & 1u;
 #ifdef JZ_GEMM_PROFILE
@@ -675,6 +702,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (chunk_end) { chunk++; in_chunk = 0; } else { in_chunk++; }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (!walk || (u += ustride) >= walk) break;
+            }
         }
         if (cs) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }   // the exchange's two cluster barriers (below)
     } else {
@@ -685,8 +714,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int half = e >> 2;        // which half of the accumulator columns
         const int lane = threadIdx.x & 31;
         float acc[HALF_N];
-#pragma unroll
-        for (int i = 0; i < HALF_N; i++) acc[i] = 0.0f;
         const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * HALF_N);
         // on the leader CTA of the pair (bit 24 of a shared-window address = low bit of the CTA's rank in its cluster); a
         // single-CTA unit keeps its own barriers -- in a cluster-split launch it has a rank of its own
@@ -706,11 +733,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int te = threadIdx.x - 32 * FIRST_EPI_WARP;
         uint32_t stage = 0, phase = 0;
         uint32_t pend_ready = 0;   // TS: `ready` barrier of the group's transformed but not yet handed-over k-block
-        int next_drain = 0;
+        int chunk_base = 0;        // chunks of the units this CTA has finished (a walk: the TMEM buffers keep alternating)
         const int kb_end = XFORM ? num_kb : 0;
 #ifdef JZ_GEMM_PROFILE
         long long pf_full = 0, pf_xf = 0, pf_dw = 0, pf_dr = 0, pf_t0 = clock64(), pf_own = 0, pf_skip = 0;
 #endif
+        Place pl = first_place;
+        for (unsigned u = unit;;) {   // one iteration unless this CTA walks a batch
+        const int m0 = pl.m0, n0 = pl.n0, bz = pl.bz;
+        int next_drain = 0;
+#pragma unroll
+        for (int i = 0; i < HALF_N; i++) acc[i] = 0.0f;
         for (int kb = 0; kb <= kb_end; kb++) {
 #ifdef JZ_GEMM_PROFILE
             const long long pf_it = clock64();
@@ -722,7 +755,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 ts_hand_over(pend_ready);
             }
             while (next_drain < num_chunks && (kb >= kb_end || (next_drain + 1) * kbc + STAGES - 1 <= kb)) {
-                const int chunk = next_drain++;
+                const int chunk = chunk_base + next_drain++;
                 const uint32_t buf = uint32_t(chunk) & 1u;
 #ifdef JZ_GEMM_PROFILE
                 const long long pf_a = clock64();
@@ -1019,6 +1052,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (blockIdx.x == 5 && blockIdx.z == 0 && lane == 0 && e == 0)
             { args.prof[24] = clock64() - pf_e0; args.prof[25] = split; args.prof[26] = args.splits; }
 #endif
+        if (!walk || (u += ustride) >= walk) break;
+        pl = place(u);              // next unit of the walk; its first k-blocks are usually in shared memory already
+        chunk_base += num_chunks;
+        }
     }
 
     tc_fence_before();
@@ -1455,13 +1492,13 @@ static int make_map_uncached(CUtensorMap* map, const Operand& op, size_t rows, s
 static bool pdl_enabled() { return pdl_on(); }
 
 // args.tiles_m / tiles_n / full_tiles / splits / kb_per_split / ws / tickets are filled by the caller (plan_units)
-template <int CG, int MODE, int TN, bool AMN, bool BMN>
+template <int CG, int MODE, int TN, bool AMN, bool BMN, bool WALK>
 static int launch_tc(const Operand& a, const Operand& b, const GemmArgs& args, unsigned batch, cudaStream_t s) {
     alignas(64) CUtensorMap ma, mb;
     int rc;
     if ((rc = make_map(&ma, a, args.m, args.k, TILE_M, batch)) != JZ_OK) return rc;
     if ((rc = make_map(&mb, b, args.n, args.k, b_rows<CG, TN>(), batch)) != JZ_OK) return rc;
-    auto kern = gemm_tcgen05_kernel<CG, MODE, TN, AMN, BMN>;
+    auto kern = gemm_tcgen05_kernel<CG, MODE, TN, AMN, BMN, WALK>;
     constexpr int SMEM = smem_bytes<CG, MODE, TN>();
     static bool attr_done = false;
     if (!attr_done) {
@@ -1473,6 +1510,10 @@ static int launch_tc(const Operand& a, const Operand& b, const GemmArgs& args, u
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(units * CG, 1, batch);
+    if (args.walk_units) {   // one CTA group per SM (pair) walks the (member, tile) units: see gemm_tc
+        const unsigned resident = unsigned(ctx().sm_count) / CG;
+        cfg.gridDim = dim3((args.walk_units < resident ? args.walk_units : resident) * CG, 1, 1);
+    }
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = s;
@@ -1555,10 +1596,21 @@ static int launch_tf32_persistent_major(const Operand& a, const Operand& b, cons
 #endif
 
 // operand majors are compile-time (they select TMA box shapes and descriptor layouts)
-template <int CG, int MODE, int TN>
+template <int CG, int MODE, int TN, bool WALK>
+static int launch_tc_major_w(const Operand& a, const Operand& b, const GemmArgs& args, unsigned batch, cudaStream_t s) {
+    if (a.mn) return b.mn ? launch_tc<CG, MODE, TN, true, true, WALK>(a, b, args, batch, s) : launch_tc<CG, MODE, TN, true, false, WALK>(a, b, args, batch, s);
+    return b.mn ? launch_tc<CG, MODE, TN, false, true, WALK>(a, b, args, batch, s) : launch_tc<CG, MODE, TN, false, false, WALK>(a, b, args, batch, s);
+}
+// WALKABLE: this (CG, MODE, TN) also exists as the unit-walking variant used for strided batches (gemm_tc asks for a walk
+// only on the variants instantiated with it, see walkable())
+template <int CG, int MODE, int TN, bool WALKABLE = true>
 static int launch_tc_major(const Operand& a, const Operand& b, const GemmArgs& args, unsigned batch, cudaStream_t s) {
-    if (a.mn) return b.mn ? launch_tc<CG, MODE, TN, true, true>(a, b, args, batch, s) : launch_tc<CG, MODE, TN, true, false>(a, b, args, batch, s);
-    return b.mn ? launch_tc<CG, MODE, TN, false, true>(a, b, args, batch, s) : launch_tc<CG, MODE, TN, false, false>(a, b, args, batch, s);
+    if constexpr (WALKABLE) {
+        if (args.walk_units) return launch_tc_major_w<CG, MODE, TN, true>(a, b, args, batch, s);
+    } else {
+        if (args.walk_units) return fail(JZ_ERR_ARG, "gemm: this kernel variant has no unit-walking form");
+    }
+    return launch_tc_major_w<CG, MODE, TN, false>(a, b, args, batch, s);
 }
 
 #endif  // JZ_GEMM_TC_IMPL
