@@ -855,10 +855,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const bool row_ok = row < args.m;
             const size_t ncol0 = size_t(n0) + half * HALF_N;
             const int slice_w = cs ? TILE_N / args.splits : TILE_N;   // cluster split: this unit finishes columns [split*w, (split+1)*w)
+            // The general column block below (beta, broadcast stage, program, peer / multicast destinations, ragged edges)
+            // is ~3.8k instructions per 32 columns, executed once per unit: ncu on a walked batch of k = 128 members
+            // showed a third of all warp samples stalled on instruction fetch there.  The common case -- C = alpha * acc
+            // into a full block of 32 columns -- takes a compact path of its own (~100 instructions).
+            const bool plain = args.beta == 0.0f && !s_chain.bias && s_chain.n == 0 && !args.mc && args.n_peers == 0;
 #pragma unroll
             for (int p = 0; p < HALF_N / 32; p++) {
                 const size_t colp = ncol0 + p * 32;
                 if (cs && (half * HALF_N + p * 32) / slice_w != split) continue;   // warp-uniform
+                if (plain && colp + 32 <= args.n) {   // warp-uniform
+                    if (row_ok) {
+                        float* dst = Cb + row + colp * ldc;
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            *dst = args.alpha * acc[p * 32 + c];
+                            dst += ldc;
+                        }
+                    }
+                    continue;
+                }
                 if (colp < args.n) {  // warp-uniform
                     const int ncols = args.n - colp < 32 ? int(args.n - colp) : 32;
                     float v[32];
@@ -1252,9 +1268,23 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                 const size_t row = size_t(u.m0) + quarter * 32 + lane;
                 const bool row_ok = row < args.m;
                 const size_t ncol0 = size_t(u.n0) + half * HALF_N;
+                // compact path for C = alpha * acc into a full block of 32 columns (see gemm_tcgen05_kernel: the general
+                // block is thousands of instructions executed once per unit, and instruction fetch shows in the samples)
+                const bool plain = args.beta == 0.0f && !s_chain.bias && s_chain.n == 0 && !args.mc && args.n_peers == 0;
 #pragma unroll
                 for (int p = 0; p < HALF_N / 32; p++) {
                     const size_t colp = ncol0 + p * 32;
+                    if (plain && colp + 32 <= args.n) {   // warp-uniform
+                        if (row_ok) {
+                            float* dst = Cb + row + colp * ldc;
+#pragma unroll
+                            for (int c = 0; c < 32; c++) {
+                                *dst = args.alpha * acc[p * 32 + c];
+                                dst += ldc;
+                            }
+                        }
+                        continue;
+                    }
                     if (colp < args.n) {  // warp-uniform
                         const int ncols = args.n - colp < 32 ? int(args.n - colp) : 32;
                         float v[32];
