@@ -200,6 +200,9 @@ int jz_gemm_last_splits(void);
 /* 1 when those k-splits were the CTAs of one thread-block cluster per tile and exchanged their partial tiles through
  * distributed shared memory (no workspace); 0 for the workspace + ticket form or no split */
 int jz_gemm_last_cluster_split(void);
+/* 1 when the last tensor-core strided batch was WALKED: one CTA (pair) per SM went through the (member, tile) units with its
+ * barriers, tensor memory and TMA pipeline alive across units, instead of one CTA per unit */
+int jz_gemm_last_walk(void);
 
 /* ---- multi-GPU, one process per GPU (SURVEY 8b jz_mg_*, 8e).  The reference has no collectives; these entry points
  *      give C / C++ callers the sharded forms without torch, NCCL or MPI inside the library: peers' buffers are mapped

@@ -89,6 +89,7 @@ _SIGS = {
                                     _F, c_size_t, _F, POINTER(jz_step), c_int, c_int, _S]),
     "jz_gemm_last_splits": (c_int, []),
     "jz_gemm_last_cluster_split": (c_int, []),
+    "jz_gemm_last_walk": (c_int, []),
     "jz_gemm_strided_batched": (c_int, [c_int, c_int, c_size_t, c_size_t, c_size_t, c_float, _F, c_size_t, c_size_t, _F, c_size_t,
                                         c_size_t, c_float, _F, c_size_t, c_size_t, c_size_t, c_int, _S]),
     "jz_mg_block_range": (c_int, [c_size_t, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]),

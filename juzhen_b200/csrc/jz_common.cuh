@@ -20,6 +20,7 @@ struct Ctx {
     int gemm_mode = JZ_GEMM_3XTF32;
     int gemm_last_path = 0;
     int gemm_last_splits = 1;   // k-splits per tail tile of the last tensor-core launch (1 = none)
+    int gemm_last_walk = 0;            // 1: the last strided batch was walked (one CTA group per SM over the (member, tile) units)
     int gemm_last_cluster_split = 0;   // 1: those splits met through distributed shared memory (one cluster per tile)
 };
 

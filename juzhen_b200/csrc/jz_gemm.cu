@@ -422,6 +422,7 @@ static int gemm_tc(int ta, int tb, size_t m, size_t n, size_t k, float alpha, co
         const bool walk = !no_walk && walkable && batch > 1 && !persist && chain.n == 0 && !chain.bias && n_peers == 0 && !mc &&
                           units_all > (unsigned long long)(ctx().sm_count / cg) && units_all < (1ull << 31);
         if (walk) args.walk_units = unsigned(units_all);
+        ctx().gemm_last_walk = walk ? 1 : 0;
         if (rc == JZ_OK) {
             const unsigned zcap = walk ? 0xFFFFFFFFu : 65535u;   // grid.z limit (a walk has no grid.z)
             for (unsigned long long b0l = 0; b0l < batch && rc == JZ_OK; b0l += zcap) {
@@ -670,6 +671,7 @@ int jz_gemm_chain_mcast(int transA, int transB, size_t m, size_t n, size_t k, fl
 
 int jz_gemm_last_splits(void) { return ctx().gemm_last_splits; }
 int jz_gemm_last_cluster_split(void) { return ctx().gemm_last_cluster_split; }
+int jz_gemm_last_walk(void) { return ctx().gemm_last_walk; }
 
 }  // extern "C"
 

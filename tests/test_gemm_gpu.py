@@ -380,3 +380,44 @@ def test_gemm_strided_batched_attention_shapes_on_tensor_cores(jz, mode, seq, dh
             A = S[h, b].T.astype(np.float64)                           # A(i, j) logical
             want = (v.T @ A.T).T                                       # H_h(d, i) = sum_j V(d, j) A(i, j) -> stored [token i][d]
             assert rel_fro(Hh[b, :, h * dh:(h + 1) * dh], want) < tol, ("H", h, b)
+
+
+@pytest.mark.parametrize("mode", ["3xtf32", "tf32"])
+@pytest.mark.parametrize("shape", [(64, 64, 128, 700, 1, 0), (100, 72, 96, 500, 0, 0), (128, 128, 64, 400, 0, 1), (256, 256, 128, 200, 1, 0),
+                                   (300, 260, 64, 100, 0, 0), (512, 512, 128, 40, 1, 0), (128, 512, 512, 100, 0, 1), (64, 520, 32, 300, 1, 1)])
+def test_gemm_strided_batched_walked_units(jz, mode, shape):
+    """strided batches with more (member, tile) units than SMs are WALKED: one CTA (pair) per SM goes through the units with
+    its barriers, tensor memory and TMA pipeline alive across them (jz_gemm_tc.cuh, WALK).  Single-CTA TMEM-A tiles and CTA
+    pairs, ragged members, every operand layout, alpha / beta (beta != 0 takes the general epilogue, beta == 0 the compact
+    one), bitwise run-to-run determinism, and the same bits as the one-CTA-per-unit launch of a batch too small to walk."""
+    m, n, k, batch, ta, tb = shape
+    md = jz._lib.GEMM_MODES[mode]
+    L = jz.lib()
+    rng = np.random.default_rng(m + 3 * n + 7 * k + batch)
+    ar, ac = (k, m) if ta else (m, k)
+    br, bc = (n, k) if tb else (k, n)
+    A = rng.standard_normal((batch, ac, ar)).astype(np.float32)      # member i = column-major (ar x ac)
+    B = rng.standard_normal((batch, bc, br)).astype(np.float32)
+    C0 = rng.standard_normal((batch, n, m)).astype(np.float32)
+    dA, dB = (jz.CM(np.asfortranarray(x.reshape(-1, 1))) for x in (A, B))
+
+    def run(alpha, beta, nb):
+        dC = jz.CM(np.asfortranarray(C0.reshape(-1, 1)))
+        jz._lib.check(L.jz_gemm_strided_batched(ta, tb, m, n, k, alpha, dA.ptr, ar, ar * ac, dB.ptr, br, br * bc, beta,
+                                                dC.ptr, m, m * n, nb, md, None))
+        return dC.to_host().ravel().reshape(batch, n, m), L.jz_gemm_last_walk(), L.jz_gemm_last_path()
+
+    for alpha, beta in ((0.7, 0.0), (1.0, -0.5)):
+        got, walked, path = run(alpha, beta, batch)
+        assert path == 1 and walked == 1, (shape, path, walked)
+        for i in list(range(0, batch, max(1, batch // 7))) + [batch - 1]:
+            a = A[i].T.astype(np.float64)            # (ar, ac) logical
+            b = B[i].T.astype(np.float64)
+            want = alpha * ((a.T if ta else a) @ (b.T if tb else b)) + beta * C0[i].T
+            assert rel_fro(got[i].T, want) < TOL[mode], (shape, alpha, beta, i)
+        again, _, _ = run(alpha, beta, batch)
+        assert np.array_equal(bits(got), bits(again))
+        few, walked_few, path_few = run(alpha, beta, 3)     # 3 members: too few units to walk -> one CTA per unit, same arithmetic
+        if path_few == 1:                                   # (tiny members of a small batch go to the small-product kernel)
+            assert walked_few == 0
+            assert np.array_equal(bits(got[:3]), bits(few[:3])), (shape, "walked vs one CTA per unit")
